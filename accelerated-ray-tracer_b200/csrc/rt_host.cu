@@ -1,0 +1,528 @@
+// rt_host.cu — host side of librt_b200.so: scene flattening + upload, device BVH build, the wave
+// loop, and the C ABI of include/rt_api.h.
+//
+// Replaces the body of the reference's scene functions (e.g. final_scene, main.cu:1178-1237):
+// cudaDeviceSetLimit(stack/heap) + cudaMallocManaged fb + curandState[nx*ny] + create_world<<<1,1>>>
+// + render_init + render + host PPM loop. No device heap, no device recursion, no managed memory.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "rt_api.h"
+#include "scene_builder.h"
+#include "rt_kernels.cuh"
+#include "rt_bvh.cuh"
+
+using namespace rt;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  return fail(std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #x); } } while (0)
+
+// ---- libdevice math service ----
+__global__ void k_devmath(int op, float x, float* out) {
+  *out = op == 0 ? sinf(x) : op == 1 ? cosf(x) : tanf(x);
+}
+struct CudaDevMath : DevMath {
+  float* d = nullptr; bool ok = true;
+  CudaDevMath() { if (cudaMalloc(&d, sizeof(float)) != cudaSuccess) ok = false; }
+  ~CudaDevMath() { if (d) cudaFree(d); }
+  float call(int op, float x) {
+    float h = 0.f;
+    k_devmath<<<1, 1>>>(op, x, d);
+    if (cudaMemcpy(&h, d, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+    return h;
+  }
+  float sinf_(float x) override { return call(0, x); }
+  float cosf_(float x) override { return call(1, x); }
+  float tanf_(float x) override { return call(2, x); }
+};
+struct HostDevMath : DevMath {  // rt_scene_export_host only
+  float sinf_(float x) override { return sinf(x); }
+  float cosf_(float x) override { return cosf(x); }
+  float tanf_(float x) override { return tanf(x); }
+};
+
+template <class T> struct DBuf {
+  T* p = nullptr; size_t n = 0;
+  cudaError_t alloc(size_t count) { free(); n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DBuf() { free(); }
+};
+
+struct rt_scene {
+  int device = 0;
+  SceneDesc sd;
+  std::vector<int> rank;
+  // flattened scene
+  DBuf<DSphere> spheres; DBuf<DQuad> quads; DBuf<DXform> xforms; DBuf<DMedium> media;
+  DBuf<DMat> mats; DBuf<DTex> texs; DBuf<DImage> images; DBuf<DTlp> tlp; DBuf<BVH4Node> nodes;
+  std::vector<unsigned char*> image_px;
+  DScene dscene;
+  int n_nodes = 0; float bvh_ms = 0.f; uint64_t h2d_bytes = 0;
+  // render state
+  cudaStream_t stream = nullptr;
+  DBuf<float4> ray_o, ray_d, thr, rad, col; DBuf<float2> hit; DBuf<uint32_t> rng;
+  DBuf<int> list0, list1, queues;
+  DBuf<WaveCounters> counters;
+  WaveCounters* h_counters = nullptr;  // pinned
+  DBuf<float> accum, fb, aov_t; DBuf<int> aov_obj, aov_mat;
+  size_t slots_cap = 0, pix_cap = 0;
+  RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
+  ~rt_scene() {
+    for (auto p : image_px) cudaFree(p);
+    if (h_counters) cudaFreeHost(h_counters);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// ---- SD -> flattened device tables ----
+struct Flattener {
+  const SceneDesc& sd;
+  std::vector<DSphere> spheres; std::vector<DQuad> quads; std::vector<DXform> xforms; std::vector<DMedium> media;
+  explicit Flattener(const SceneDesc& s) : sd(s) {}
+  static DQuad mkquad(const rt_object_desc& o) {
+    DQuad q;
+    q.Qx = o.Q[0]; q.Qy = o.Q[1]; q.Qz = o.Q[2]; q.D = o.D;
+    q.ux = o.u[0]; q.uy = o.u[1]; q.uz = o.u[2]; q.mat = o.mat;
+    q.vx = o.v[0]; q.vy = o.v[1]; q.vz = o.v[2]; q.pad0 = 0;
+    q.wx = o.w[0]; q.wy = o.w[1]; q.wz = o.w[2]; q.pad1 = 0;
+    q.nx = o.n[0]; q.ny = o.n[1]; q.nz = o.n[2]; q.pad2 = 0;
+    return q;
+  }
+  uint32_t flatten(int id) {
+    const rt_object_desc& o = sd.obj[id];
+    switch (o.kind) {
+      case RT_OBJ_SPHERE: {
+        DSphere s; s.cx = o.c0[0]; s.cy = o.c0[1]; s.cz = o.c0[2]; s.radius = o.radius;
+        s.dx = o.dc[0]; s.dy = o.dc[1]; s.dz = o.dc[2]; s.mat = o.mat;
+        spheres.push_back(s);
+        return make_ref(G_SPHERE, (uint32_t)spheres.size() - 1);
+      }
+      case RT_OBJ_QUAD:
+        quads.push_back(mkquad(o));
+        return make_ref(G_QUAD, (uint32_t)quads.size() - 1);
+      case RT_OBJ_BOX: {
+        uint32_t first = (uint32_t)quads.size();
+        for (int i = 0; i < 6; ++i) quads.push_back(mkquad(sd.obj[o.child + i]));
+        return make_ref(G_BOX, first);
+      }
+      case RT_OBJ_TRANSLATE: {
+        DXform x; memset(&x, 0, sizeof(x));
+        x.kind = X_TRANSLATE; x.child = flatten(o.child); x.a = o.offset[0]; x.b = o.offset[1]; x.c = o.offset[2];
+        xforms.push_back(x);
+        return make_ref(G_XFORM, (uint32_t)xforms.size() - 1);
+      }
+      case RT_OBJ_ROTATE_Y: {
+        DXform x; memset(&x, 0, sizeof(x));
+        x.kind = X_ROTATE_Y; x.child = flatten(o.child); x.a = o.sin_t; x.b = o.cos_t;
+        xforms.push_back(x);
+        return make_ref(G_XFORM, (uint32_t)xforms.size() - 1);
+      }
+      case RT_OBJ_MEDIUM: {
+        DMedium m; m.boundary = flatten(o.child); m.neg_inv_density = o.neg_inv_density; m.mat = o.mat; m.pad = 0;
+        media.push_back(m);
+        return make_ref(G_MEDIUM, (uint32_t)media.size() - 1);
+      }
+    }
+    return make_ref(G_SPHERE, 0);
+  }
+};
+
+static bool tex_needs_uv(const SceneDesc& sd, int t, int depth = 0) {
+  if (t < 0 || depth > 8) return false;
+  const rt_texture_desc& d = sd.tex[t];
+  if (d.kind == RT_TEX_IMAGE || d.kind == RT_TEX_UV_OFFSET) return true;
+  if (d.kind == RT_TEX_CHECKER) return tex_needs_uv(sd, d.even, depth + 1) || tex_needs_uv(sd, d.odd, depth + 1);
+  return false;
+}
+
+static int queue_of(int mat_kind) {
+  switch (mat_kind) {
+    case RT_MAT_LAMBERTIAN: return Q_LAMBERTIAN;
+    case RT_MAT_METAL: return Q_METAL;
+    case RT_MAT_DIELECTRIC: return Q_DIELECTRIC;
+    case RT_MAT_DIFFUSE_LIGHT: return Q_LIGHT;
+    default: return Q_ISOTROPIC;
+  }
+}
+
+static int upload_scene(rt_scene* s) {
+  const SceneDesc& sd = s->sd;
+  Flattener F(sd);
+  const int n = (int)sd.top.size();
+  std::vector<DTlp> tlp(n);
+  std::vector<BuildBox> boxes(n);
+  std::vector<uint32_t> refs(n);
+  for (int k = 0; k < n; ++k) {
+    const rt_object_desc& o = sd.obj[sd.top[k]];
+    tlp[k].ref = F.flatten(sd.top[k]);
+    tlp[k].mat = o.mat;
+    tlp[k].queue = queue_of(sd.mat[o.mat].kind);
+    tlp[k].rank = s->rank[k];
+    refs[k] = tlp[k].ref;
+    for (int a = 0; a < 3; ++a) { boxes[k].mn[a] = o.box_min[a]; boxes[k].mx[a] = o.box_max[a]; }
+  }
+  std::vector<DMat> mats(sd.mat.size());
+  for (size_t i = 0; i < sd.mat.size(); ++i) {
+    const rt_material_desc& m = sd.mat[i];
+    DMat d; memset(&d, 0, sizeof(d));
+    d.kind = m.kind; d.tex = m.tex; d.ax = m.albedo[0]; d.ay = m.albedo[1]; d.az = m.albedo[2]; d.param = m.param;
+    d.needs_uv = tex_needs_uv(sd, m.tex) ? 1 : 0;
+    mats[i] = d;
+  }
+  std::vector<DTex> texs(sd.tex.size());
+  for (size_t i = 0; i < sd.tex.size(); ++i) {
+    const rt_texture_desc& t = sd.tex[i];
+    DTex d; memset(&d, 0, sizeof(d));
+    d.kind = t.kind; d.even = t.even; d.odd = t.odd; d.image = t.image;
+    d.cx = t.color[0]; d.cy = t.color[1]; d.cz = t.color[2]; d.scale = t.scale;
+    for (int k = 0; k < 13; ++k) d.p[k] = t.p[k];
+    texs[i] = d;
+  }
+  std::vector<DImage> images(sd.img.size());
+  uint64_t bytes = 0;
+  for (size_t i = 0; i < sd.img.size(); ++i) {
+    const HostImage& im = sd.img_data[i];
+    unsigned char* d = nullptr;
+    CU(cudaMalloc(&d, im.px.size()));
+    CU(cudaMemcpy(d, im.px.data(), im.px.size(), cudaMemcpyHostToDevice));
+    s->image_px.push_back(d);
+    images[i].data = d; images[i].width = im.width; images[i].height = im.height; images[i].bpp = im.bpp; images[i].pad = 0;
+    bytes += im.px.size();
+  }
+  CU(s->spheres.upload(F.spheres)); CU(s->quads.upload(F.quads)); CU(s->xforms.upload(F.xforms)); CU(s->media.upload(F.media));
+  CU(s->mats.upload(mats)); CU(s->texs.upload(texs)); CU(s->images.upload(images)); CU(s->tlp.upload(tlp));
+  bytes += F.spheres.size() * sizeof(DSphere) + F.quads.size() * sizeof(DQuad) + F.xforms.size() * sizeof(DXform) +
+           F.media.size() * sizeof(DMedium) + mats.size() * sizeof(DMat) + texs.size() * sizeof(DTex) +
+           images.size() * sizeof(DImage) + tlp.size() * sizeof(DTlp) + boxes.size() * sizeof(BuildBox) + refs.size() * 4;
+
+  // ---- BVH build on the device ----
+  DBuf<BuildBox> d_boxes; DBuf<uint32_t> d_refs;
+  CU(d_boxes.upload(boxes)); CU(d_refs.upload(refs));
+  CU(s->nodes.alloc(std::max(n, 1)));
+  DBuf<int> d_nout; CU(d_nout.alloc(1));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0));
+  if (n <= 1) {
+    k_bvh_trivial<<<1, 1>>>(n, d_boxes.p, d_refs.p, s->nodes.p, d_nout.p);
+  } else {
+    const int B = 256, G = (n + B - 1) / B;
+    DBuf<unsigned int> cb; CU(cb.alloc(6));
+    unsigned int init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    CU(cudaMemcpy(cb.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    DBuf<unsigned long long> k_in, k_out; DBuf<int> v_in, v_out;
+    CU(k_in.alloc(n)); CU(k_out.alloc(n)); CU(v_in.alloc(n)); CU(v_out.alloc(n));
+    k_bvh_bounds<<<G, B>>>(d_boxes.p, n, cb.p);
+    k_bvh_morton<<<G, B>>>(d_boxes.p, n, cb.p, k_in.p, v_in.p);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, n, 0, 63);
+    DBuf<unsigned char> tmp; CU(tmp.alloc(tmp_bytes));
+    cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, n, 0, 63);
+    DBuf<int> left, right, parent, flags; DBuf<BuildBox> nbox; DBuf<int2> qa, qb;
+    CU(left.alloc(n)); CU(right.alloc(n)); CU(parent.alloc(2 * n)); CU(flags.alloc(n)); CU(nbox.alloc(2 * n));
+    CU(qa.alloc(n)); CU(qb.alloc(n));
+    CU(cudaMemset(flags.p, 0, n * sizeof(int)));
+    k_bvh_karras<<<G, B>>>(k_out.p, n, left.p, right.p, parent.p);
+    k_bvh_fit<<<G, B>>>(d_boxes.p, v_out.p, n, left.p, right.p, parent.p, nbox.p, flags.p);
+    k_bvh_collapse<<<1, 1024>>>(n, left.p, right.p, nbox.p, v_out.p, d_refs.p, s->nodes.p, d_nout.p, qa.p, qb.p);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  }
+  CU(cudaEventRecord(e1));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  CU(cudaEventElapsedTime(&s->bvh_ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU(cudaMemcpy(&s->n_nodes, d_nout.p, sizeof(int), cudaMemcpyDeviceToHost));
+  s->h2d_bytes = bytes;
+
+  DScene& D = s->dscene;
+  D.spheres = s->spheres.p; D.quads = s->quads.p; D.xforms = s->xforms.p; D.media = s->media.p;
+  D.mats = s->mats.p; D.texs = s->texs.p; D.images = s->images.p; D.tlp = s->tlp.p; D.nodes = s->nodes.p;
+  D.n_tlp = n; D.n_nodes = s->n_nodes;
+  const rt_camera_desc& c = sd.cam;
+  D.cam.origin = v3(c.origin[0], c.origin[1], c.origin[2]);
+  D.cam.llc = v3(c.lower_left_corner[0], c.lower_left_corner[1], c.lower_left_corner[2]);
+  D.cam.horizontal = v3(c.horizontal[0], c.horizontal[1], c.horizontal[2]);
+  D.cam.vertical = v3(c.vertical[0], c.vertical[1], c.vertical[2]);
+  D.cam.u = v3(c.u[0], c.u[1], c.u[2]);
+  D.cam.v = v3(c.v[0], c.v[1], c.v[2]);
+  D.cam.lens_radius = c.lens_radius; D.cam.time0 = c.time0; D.cam.time1 = c.time1;
+  return 0;
+}
+
+// ---- C ABI ----
+extern "C" const char* rt_last_error(void) { return g_err.c_str(); }
+
+extern "C" int rt_build_scene(const rt_scene_desc* desc, rt_scene** out) {
+  if (!desc || !out) return fail("rt_build_scene: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("rt_build_scene: no CUDA device (this library has no CPU path)");
+  int dev = desc->device;
+  if (dev < 0) { CU(cudaGetDevice(&dev)); }
+  CU(cudaSetDevice(dev));
+  rt_scene* s = new rt_scene();
+  s->device = dev;
+  {
+    CudaDevMath dm;
+    std::string err = generate_scene(s->sd, dm, desc->scene_id, desc->nx, desc->ny, desc->grid_half,
+                                     desc->texture_dir ? desc->texture_dir : "");
+    if (!err.empty()) { delete s; return fail("rt_build_scene: " + err); }
+    if (!dm.ok) { delete s; return fail("rt_build_scene: device math service failed"); }
+  }
+  s->rank = reference_leaf_order(s->sd);
+  if (upload_scene(s)) { delete s; return 1; }
+  if (cudaStreamCreate(&s->stream) != cudaSuccess) { delete s; return fail("cudaStreamCreate failed"); }
+  if (cudaMallocHost(&s->h_counters, sizeof(WaveCounters)) != cudaSuccess) { delete s; return fail("cudaMallocHost failed"); }
+  *out = s;
+  return 0;
+}
+
+extern "C" void rt_destroy(rt_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  delete s;
+}
+
+extern "C" int rt_scene_info_get(rt_scene* s, rt_scene_info* o) {
+  if (!s || !o) return fail("rt_scene_info_get: null argument");
+  memset(o, 0, sizeof(*o));
+  o->scene_id = s->sd.scene_id; o->nx = s->sd.nx; o->ny = s->sd.ny;
+  o->n_top = (int)s->sd.top.size(); o->n_obj = (int)s->sd.obj.size(); o->n_mat = (int)s->sd.mat.size();
+  o->n_tex = (int)s->sd.tex.size(); o->n_img = (int)s->sd.img.size(); o->n_bvh_nodes = s->n_nodes;
+  o->default_nx = s->sd.default_nx; o->default_ny = s->sd.default_ny; o->default_spp = s->sd.default_spp;
+  o->gradient_bg = s->sd.gradient_bg;
+  for (int k = 0; k < 3; ++k) o->background[k] = s->sd.background[k];
+  o->bvh_build_ms = s->bvh_ms; o->h2d_bytes = s->h2d_bytes;
+  return 0;
+}
+
+static int export_sd(const SceneDesc& sd, const std::vector<int>& rank, void* buf, size_t cap, size_t* needed,
+                     int32_t* rank_out, int rank_cap) {
+  std::string bin = sd_serialize(sd);
+  if (needed) *needed = bin.size();
+  if (buf && cap >= bin.size()) memcpy(buf, bin.data(), bin.size());
+  if (rank_out) for (int k = 0; k < (int)rank.size() && k < rank_cap; ++k) rank_out[k] = rank[k];
+  return 0;
+}
+extern "C" int rt_scene_export(rt_scene* s, void* buf, size_t cap, size_t* needed, int32_t* rank) {
+  if (!s) return fail("rt_scene_export: null scene");
+  return export_sd(s->sd, s->rank, buf, cap, needed, rank, (int)s->rank.size());
+}
+extern "C" int rt_scene_export_host(const rt_scene_desc* desc, void* buf, size_t cap, size_t* needed, int32_t* rank,
+                                    int32_t rank_cap) {
+  if (!desc) return fail("rt_scene_export_host: null argument");
+  HostDevMath dm;
+  SceneDesc sd;
+  std::string err = generate_scene(sd, dm, desc->scene_id, desc->nx, desc->ny, desc->grid_half,
+                                   desc->texture_dir ? desc->texture_dir : "");
+  if (!err.empty()) return fail("rt_scene_export_host: " + err);
+  std::vector<int> rk = reference_leaf_order(sd);
+  return export_sd(sd, rk, buf, cap, needed, rank, rank_cap);
+}
+
+static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rng, bool aov) {
+  if (n_slots > s->slots_cap) {
+    CU(s->ray_o.alloc(n_slots)); CU(s->ray_d.alloc(n_slots)); CU(s->thr.alloc(n_slots)); CU(s->rad.alloc(n_slots));
+    CU(s->col.alloc(n_slots)); CU(s->hit.alloc(n_slots)); CU(s->list0.alloc(n_slots)); CU(s->list1.alloc(n_slots));
+    CU(s->queues.alloc(n_slots * Q_COUNT));
+    s->rng.free();
+    s->slots_cap = n_slots;
+  }
+  if (ref_rng && s->rng.n < 6 * n_slots) CU(s->rng.alloc(6 * s->slots_cap));
+  if (n_pix > s->pix_cap) {
+    CU(s->accum.alloc(3 * n_pix)); CU(s->fb.alloc(3 * n_pix));
+    s->aov_obj.free(); s->aov_mat.free(); s->aov_t.free();
+    s->pix_cap = n_pix;
+  }
+  if (aov && s->aov_obj.n < n_pix) { CU(s->aov_obj.alloc(s->pix_cap)); CU(s->aov_mat.alloc(s->pix_cap)); CU(s->aov_t.alloc(s->pix_cap)); }
+  if (!s->counters.p) CU(s->counters.alloc(1));
+  return 0;
+}
+
+extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_ms, uint64_t* rays) {
+  if (!s || !p) return fail("rt_render: null argument");
+  CU(cudaSetDevice(s->device));
+  const SceneDesc& sd = s->sd;
+  const int spp_total = p->spp > 0 ? p->spp : sd.default_spp;
+  const int world = p->world > 0 ? p->world : 1, rank = p->rank;
+  if (rank < 0 || rank >= world) return fail("rt_render: rank out of range");
+  const bool ref_rng = p->rng_mode == 1;
+  if (ref_rng && p->split_mode == 1 && world > 1)
+    return fail("rt_render: reference-RNG mode cannot split a pixel's samples across ranks (one sequential stream per pixel)");
+  RenderParams P; memset(&P, 0, sizeof(P));
+  P.nx = sd.nx; P.ny = sd.ny;
+  if (p->split_mode == 1) {  // spp split: all pixels, a share of the samples
+    P.rank = 0; P.world = 1; P.rows_local = sd.ny;
+    const int base = (int)((long long)spp_total * rank / world), end = (int)((long long)spp_total * (rank + 1) / world);
+    P.sample_base = base; P.sample_count = end - base;
+  } else {  // tile split: scanlines j = rank (mod world), all samples
+    P.rank = rank; P.world = world; P.rows_local = (sd.ny - rank + world - 1) / world;
+    P.sample_base = 0; P.sample_count = spp_total;
+  }
+  const size_t n_pix = (size_t)P.rows_local * P.nx;
+  int S = p->substreams;
+  if (S <= 0) {
+    long long target = 2 * 1024 * 1024;
+    if (const char* e = getenv("RT_SLOTS")) target = atoll(e);
+    S = (int)std::max<long long>(1, (target + (long long)n_pix / 2) / std::max<size_t>(n_pix, 1));
+  }
+  if (ref_rng) S = 1;
+  S = std::max(1, std::min(S, std::max(P.sample_count, 1)));
+  P.substreams = S;
+  P.n_slots = (int)(n_pix * S);
+  P.max_depth = p->max_depth > 0 ? p->max_depth : 50;
+  P.tmin = p->t_min > 0 ? p->t_min : 0.001f;
+  if (p->override_background) { P.background = v3(p->background[0], p->background[1], p->background[2]); P.gradient = p->gradient_bg; }
+  else { P.background = v3(sd.background[0], sd.background[1], sd.background[2]); P.gradient = sd.gradient_bg; }
+  P.seed = p->seed ? p->seed : 1984ull;
+  const float gamma = p->gamma > 0 ? p->gamma : 2.2f;
+  if (ensure_buffers(s, P.n_slots, n_pix, ref_rng, p->aov != 0)) return 1;
+
+  PathArrays A;
+  A.ray_o = s->ray_o.p; A.ray_d = s->ray_d.p; A.hit = s->hit.p; A.thr = s->thr.p; A.rad = s->rad.p; A.col = s->col.p;
+  A.rng = s->rng.p;
+  cudaStream_t st = s->stream;
+  cudaEvent_t e0, e1, ev;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU(cudaMemsetAsync(s->counters.p, 0, sizeof(WaveCounters), st));
+  CU(cudaEventRecord(e0, st));
+  const int B = 128;
+  int launches = 0, waves = 0;
+  if (P.n_slots > 0 && P.sample_count > 0) {
+    const int G = (P.n_slots + B - 1) / B;
+    if (ref_rng) k_start<RNG_REFERENCE><<<G, B, 0, st>>>(s->dscene, P, A, s->list0.p, s->counters.p);
+    else k_start<RNG_PHILOX><<<G, B, 0, st>>>(s->dscene, P, A, s->list0.p, s->counters.p);
+    ++launches;
+    int bound = P.n_slots;  // the live-ray count never grows: the last known value bounds the grid
+    int batch = 8;
+    if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
+    int parity = 0;
+    while (bound > 0) {
+      for (int w = 0; w < batch; ++w) {
+        const int Gt = (bound + B - 1) / B;
+        const int Gs = (bound + 32 * Q_COUNT + B - 1) / B;
+        int* cur = parity ? s->list1.p : s->list0.p;
+        int* nxt = parity ? s->list0.p : s->list1.p;
+        k_trace<<<Gt, B, 0, st>>>(s->dscene, P, A, cur, s->queues.p, s->counters.p, parity);
+        if (ref_rng) k_shade<RNG_REFERENCE><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, nxt, s->counters.p, parity);
+        else k_shade<RNG_PHILOX><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, nxt, s->counters.p, parity);
+        parity ^= 1; launches += 2; ++waves;
+      }
+      CU(cudaMemcpyAsync(s->h_counters, s->counters.p, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+      CU(cudaEventRecord(ev, st));
+      CU(cudaEventSynchronize(ev));
+      bound = s->h_counters->n_active[parity];
+    }
+  }
+  {
+    const int Gp = (int)((n_pix + 255) / 256);
+    if (n_pix > 0) {
+      k_accumulate<<<Gp, 256, 0, st>>>(P, A, s->accum.p);
+      k_resolve<<<Gp, 256, 0, st>>>((int)n_pix, spp_total, gamma, s->accum.p, s->fb.p);
+      launches += 2;
+    }
+  }
+  CU(cudaEventRecord(e1, st));
+  if (p->aov && n_pix > 0) {
+    k_aov<<<(int)((n_pix + B - 1) / B), B, 0, st>>>(s->dscene, P, s->aov_obj.p, s->aov_mat.p, s->aov_t.p, s->counters.p);
+  }
+  CU(cudaMemcpyAsync(s->h_counters, s->counters.p, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ev);
+  s->last = P; s->has_aov = p->aov != 0; s->last_gamma = gamma; s->last_spp_total = spp_total;
+  rt_render_stats& R = s->stats;
+  memset(&R, 0, sizeof(R));
+  R.device_ms = ms; R.rays = s->h_counters->rays; R.samples = (uint64_t)n_pix * (uint64_t)P.sample_count;
+  R.waves = waves; R.kernel_launches = launches; R.rows_local = P.rows_local; R.nx = P.nx;
+  R.substreams = S; R.n_slots = P.n_slots; R.stack_overflow = s->h_counters->overflow;
+  if (device_ms) *device_ms = ms;
+  if (rays) *rays = R.rays;
+  if (R.stack_overflow) return fail("rt_render: BVH traversal stack overflow (RT_STACK too small for this scene)");
+  return 0;
+}
+
+extern "C" int rt_render_stats_get(rt_scene* s, rt_render_stats* out) {
+  if (!s || !out) return fail("rt_render_stats_get: null argument");
+  *out = s->stats;
+  return 0;
+}
+
+extern "C" int rt_readback(rt_scene* s, float* rgb, int32_t* obj_id, int32_t* mat_id) {
+  if (!s) return fail("rt_readback: null scene");
+  CU(cudaSetDevice(s->device));
+  const size_t n_pix = (size_t)s->last.rows_local * s->last.nx;
+  if (n_pix == 0) return 0;
+  if (rgb) CU(cudaMemcpy(rgb, s->fb.p, n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (obj_id || mat_id) {
+    if (!s->has_aov) return fail("rt_readback: the last rt_render had aov = 0");
+    if (obj_id) CU(cudaMemcpy(obj_id, s->aov_obj.p, n_pix * sizeof(int), cudaMemcpyDeviceToHost));
+    if (mat_id) CU(cudaMemcpy(mat_id, s->aov_mat.p, n_pix * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+extern "C" int rt_readback_t(rt_scene* s, float* t) {
+  if (!s || !t) return fail("rt_readback_t: null argument");
+  if (!s->has_aov) return fail("rt_readback_t: the last rt_render had aov = 0");
+  CU(cudaSetDevice(s->device));
+  const size_t n_pix = (size_t)s->last.rows_local * s->last.nx;
+  if (n_pix) CU(cudaMemcpy(t, s->aov_t.p, n_pix * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int rt_accum_device_ptr(rt_scene* s, void** dptr, size_t* n_floats) {
+  if (!s || !dptr) return fail("rt_accum_device_ptr: null argument");
+  *dptr = s->accum.p;
+  if (n_floats) *n_floats = (size_t)s->last.rows_local * s->last.nx * 3;
+  return 0;
+}
+extern "C" int rt_resolve(rt_scene* s, int32_t total_spp, float gamma) {
+  if (!s) return fail("rt_resolve: null scene");
+  CU(cudaSetDevice(s->device));
+  const size_t n_pix = (size_t)s->last.rows_local * s->last.nx;
+  if (n_pix == 0) return 0;
+  k_resolve<<<(int)((n_pix + 255) / 256), 256, 0, s->stream>>>((int)n_pix, total_spp > 0 ? total_spp : s->last_spp_total,
+                                                              gamma > 0 ? gamma : s->last_gamma, s->accum.p, s->fb.p);
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" long rt_write_ppm(const char* path, const float* rgb, int32_t nx, int32_t ny, int32_t double_scale) {
+  if (!rgb || nx <= 0 || ny <= 0) { fail("rt_write_ppm: bad argument"); return -1; }
+  FILE* f = path ? fopen(path, "w") : stdout;
+  if (!f) { fail("rt_write_ppm: cannot open output"); return -1; }
+  std::string out;
+  out.reserve((size_t)nx * ny * 12 + 32);
+  char line[64];
+  snprintf(line, sizeof(line), "P3\n%d %d\n255\n", nx, ny);
+  out += line;
+  for (int j = ny - 1; j >= 0; j--)
+    for (int i = 0; i < nx; i++) {
+      const float* c = rgb + 3 * ((size_t)j * nx + i);
+      int ir, ig, ib;
+      if (double_scale) { ir = int(255.99 * c[0]); ig = int(255.99 * c[1]); ib = int(255.99 * c[2]); }
+      else { ir = int(255.99f * c[0]); ig = int(255.99f * c[1]); ib = int(255.99f * c[2]); }
+      snprintf(line, sizeof(line), "%d %d %d\n", ir, ig, ib);
+      out += line;
+    }
+  size_t w = fwrite(out.data(), 1, out.size(), f);
+  if (path) fclose(f); else fflush(f);
+  return (long)w;
+}

@@ -1,0 +1,305 @@
+// rt_kernels.cuh — the wavefront render kernels (device only).
+//
+// The reference renders with ONE megakernel: a thread per pixel loops ns samples x <= 50 bounces
+// through virtual calls and device recursion (render/color, main.cu:44-133). Here the same
+// integrator runs as waves over a pool of path slots kept in SoA arrays in HBM/L2:
+//
+//   k_start    every slot draws its first camera ray                         (main.cu:119-123)
+//   k_trace    closest hit of every live ray over the 4-wide BVH; paths are binned by the hit
+//              material class into shade queues (warp-aggregated atomics)   (main.cu:57; bvh.cuh:95)
+//   k_shade    one material class per warp: miss/background, emission, scatter, throughput;
+//              finished samples are folded into the slot's sum and the slot draws its next
+//              camera ray in place (path regeneration); survivors are compacted into the
+//              next wave's ray list                                          (main.cu:58-83, 119-125)
+//   k_resolve  per pixel: sum the slot partials, scale by 1/ns, gamma        (main.cu:128-132)
+//   k_aov      primary-hit object/material id + t for the centre ray of every pixel
+//
+// A slot is bound to one pixel and one sub-stream q of that pixel's samples (samples q, q+S, ...),
+// so per-pixel sums need no atomics and are deterministic. In reference-RNG mode S = 1 and a slot
+// consumes its pixel's XORWOW stream in exactly the reference's order.
+#pragma once
+#include "rt_shade.cuh"
+
+namespace rt {
+
+struct PathArrays {
+  float4* ray_o;   // origin.xyz, time
+  float4* ray_d;   // direction.xyz, -
+  float2* hit;     // t, top-level object index (int bits; -1 = miss)
+  float4* thr;     // throughput.rgb, bounce (int bits)
+  float4* rad;     // radiance.rgb of the current sample, sample number (int bits)
+  float4* col;     // sum of finished samples.rgb, -
+  uint32_t* rng;   // reference-RNG mode: 6 words per slot, SoA [6][n_slots]
+};
+
+struct WaveCounters {
+  int n_active[2];             // live rays in list[parity]
+  int n_queue[2][Q_COUNT + 2]; // shade queue fill, by wave parity
+  unsigned long long rays;     // closest-hit queries issued (= the reference's bounce-loop iterations)
+  unsigned long long samples;  // finished samples
+  unsigned int overflow;       // traversal stack overflow flag (must stay 0)
+  int pad;
+};
+
+struct RenderParams {
+  int nx, ny;            // full image
+  int rows_local;        // scanlines owned by this rank (tile split: j = lr * world + rank)
+  int rank, world;
+  int n_slots;           // rows_local * nx * substreams
+  int substreams;        // S
+  int sample_base;       // first sample number of this rank's share (spp split), else 0
+  int sample_count;      // samples per pixel this rank renders
+  int max_depth;         // 50
+  float tmin;            // 0.001f
+  V3 background; int gradient;
+  unsigned long long seed;  // 1984
+};
+
+enum RngMode : int { RNG_PHILOX = 0, RNG_REFERENCE = 1 };
+
+struct SlotInfo { int lpix, i, j, pix, sub; };
+RT_D SlotInfo slot_info(const RenderParams& P, int slot) {
+  SlotInfo s;
+  const int npl = P.rows_local * P.nx;
+  s.sub = slot / npl;
+  s.lpix = slot - s.sub * npl;
+  const int lr = s.lpix / P.nx;
+  s.i = s.lpix - lr * P.nx;
+  s.j = lr * P.world + P.rank;
+  s.pix = s.j * P.nx + s.i;  // the reference's pixel_index (main.cu:115)
+  return s;
+}
+
+template <int MODE> struct RngOf;
+template <> struct RngOf<RNG_PHILOX> { typedef Philox type; };
+template <> struct RngOf<RNG_REFERENCE> { typedef Xorwow type; };
+
+template <int MODE>
+RT_D void rng_load(typename RngOf<MODE>::type& g, const PathArrays& A, const RenderParams& P, int slot, int pix, int sample, int stage);
+template <>
+RT_D void rng_load<RNG_PHILOX>(Philox& g, const PathArrays&, const RenderParams& P, int, int pix, int sample, int stage) {
+  g.init(P.seed, (uint32_t)pix, (uint32_t)sample, (uint32_t)stage);
+}
+template <>
+RT_D void rng_load<RNG_REFERENCE>(Xorwow& g, const PathArrays& A, const RenderParams& P, int slot, int, int, int) {
+  const int n = P.n_slots;
+  g.d = A.rng[slot]; g.v0 = A.rng[n + slot]; g.v1 = A.rng[2 * n + slot]; g.v2 = A.rng[3 * n + slot];
+  g.v3 = A.rng[4 * n + slot]; g.v4 = A.rng[5 * n + slot];
+}
+RT_D void rng_store(const Philox&, const PathArrays&, const RenderParams&, int) {}
+RT_D void rng_store(const Xorwow& g, const PathArrays& A, const RenderParams& P, int slot) {
+  const int n = P.n_slots;
+  A.rng[slot] = g.d; A.rng[n + slot] = g.v0; A.rng[2 * n + slot] = g.v1; A.rng[3 * n + slot] = g.v2;
+  A.rng[4 * n + slot] = g.v3; A.rng[5 * n + slot] = g.v4;
+}
+
+// New camera sample for a slot (main.cu:121-123): jitter, lens, shutter time; throughput 1, radiance 0.
+template <class RNG>
+RT_D void start_sample(const DScene& S, const RenderParams& P, const PathArrays& A, int slot, const SlotInfo& si, int sample, RNG& g) {
+  const float u = fdiv(fadd((float)si.i, g.uniform()), (float)P.nx);
+  const float v = fdiv(fadd((float)si.j, g.uniform()), (float)P.ny);
+  Ray r = camera_get_ray(S.cam, u, v, g);
+  A.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
+  A.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);
+  A.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
+  A.rad[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(sample));
+}
+
+// Warp-aggregated append: lanes with `pred` get consecutive positions in a global list.
+RT_D int warp_append(int* counter, bool pred) {
+  const unsigned m = __ballot_sync(__activemask(), pred);
+  if (!pred) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_start(DScene S, RenderParams P, PathArrays A, int* list0, WaveCounters* C) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= P.n_slots) return;
+  const SlotInfo si = slot_info(P, slot);
+  A.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+  typename RngOf<MODE>::type g;
+  if constexpr (MODE == RNG_REFERENCE) { g.init((unsigned long long)(long long)(1984 + si.pix)); }  // render_init, main.cu:104
+  const bool live = si.sub < P.sample_count;
+  if (live) {
+    const int sample = P.sample_base + si.sub;
+    if constexpr (MODE == RNG_PHILOX) rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
+    start_sample(S, P, A, slot, si, sample, g);
+  }
+  if constexpr (MODE == RNG_REFERENCE) rng_store(g, A, P, slot);
+  const int pos = warp_append(&C->n_active[0], live);
+  if (live) list0[pos] = slot;
+}
+
+__global__ void __launch_bounds__(128) k_trace(DScene S, RenderParams P, PathArrays A, const int* __restrict__ list,
+                                               int* __restrict__ queues, WaveCounters* C, int parity) {
+  const int n = C->n_active[parity];
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    C->n_active[parity ^ 1] = 0;  // the shade kernel of this wave appends here
+    C->rays += (unsigned long long)n;
+  }
+  if (gid >= n) return;
+  const int slot = list[gid];
+  const float4 o = A.ray_o[slot], d = A.ray_d[slot];
+  Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+  const Hit h = closest_hit(S, r, P.tmin, FLT_MAX, &C->overflow);
+  A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp));
+  const int q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
+  // bin by material class: one warp-aggregated atomic per class present in the warp
+#pragma unroll
+  for (int k = 0; k < Q_COUNT; ++k) {
+    const int pos = warp_append(&C->n_queue[parity][k], q == k);
+    if (q == k) queues[(size_t)k * P.n_slots + pos] = slot;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_shade(DScene S, RenderParams P, PathArrays A, const int* __restrict__ queues,
+                                               int* __restrict__ next_list, WaveCounters* C, int parity) {
+  // thread -> (queue, position): queues are laid end to end, each padded to a whole warp
+  int cnt[Q_COUNT];
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < Q_COUNT; ++k) { cnt[k] = C->n_queue[parity][k]; total += (cnt[k] + 31) & ~31; }
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < Q_COUNT; ++k) C->n_queue[parity ^ 1][k] = 0;  // next wave's trace fills these
+  }
+  if (gid >= total) return;
+  int q = 0, base = 0, qcount = cnt[0];
+#pragma unroll
+  for (int k = 0; k < Q_COUNT - 1; ++k) {
+    const int padded = (cnt[k] + 31) & ~31;
+    if (q == k && gid >= base + padded) { base += padded; q = k + 1; qcount = cnt[k + 1]; }
+  }
+  const int pos = gid - base;
+  const bool valid = pos < qcount;
+  bool alive = false;
+  int slot = -1;
+  if (valid) {
+    slot = queues[(size_t)q * P.n_slots + pos];
+    const SlotInfo si = slot_info(P, slot);
+    const float4 o = A.ray_o[slot], d = A.ray_d[slot];
+    float4 thr4 = A.thr[slot], rad4 = A.rad[slot];
+    Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+    V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(rad4.x, rad4.y, rad4.z);
+    int bounce = __float_as_int(thr4.w);
+    int sample = __float_as_int(rad4.w);
+    typename RngOf<MODE>::type g;
+    rng_load<MODE>(g, A, P, slot, si.pix, sample, bounce + 1);
+    bool sample_done;
+    Ray next; next.o = r.o; next.d = r.d; next.tm = r.tm;
+    if (q == Q_MISS) {
+      // main.cu:58-68
+      V3 bg = P.background;
+      if (P.gradient) {
+        const float uy = fdiv(r.d.y, vlen(r.d));
+        const float t = fmul(0.5f, fadd(uy, 1.0f));
+        const float omt = fsub(1.0f, t);
+        bg = v3(ffma(t, 0.5f, omt), ffma(t, 0.7f, omt), fadd(t, omt));
+      }
+      rad = v3(ffma(thr.x, bg.x, rad.x), ffma(thr.y, bg.y, rad.y), ffma(thr.z, bg.z, rad.z));
+      sample_done = true;
+    } else {
+      const float2 hh = A.hit[slot];
+      const int tlp = __float_as_int(hh.y);
+      const DTlp T = S.tlp[tlp];
+      const DMat m = S.mats[T.mat];
+      Rec rec;
+      if (ref_type(T.ref) == G_MEDIUM) {  // constant_medium.cuh:58-62
+        rec.t = hh.x;
+        rec.p = vmad(hh.x, r.d, r.o);
+        rec.n = v3(1, 0, 0);
+        rec.u = rec.v = 0.f;
+      } else {
+        geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec);
+      }
+      if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
+        const V3 e = material_emitted(S, m, rec);
+        rad = v3(ffma(thr.x, e.x, rad.x), ffma(thr.y, e.y, rad.y), ffma(thr.z, e.z, rad.z));
+      }
+      V3 att;
+      const bool scattered = material_scatter(S, m, r, rec, g, att, next);  // main.cu:76
+      if (scattered) {
+        thr = vmul(thr, att);  // main.cu:82
+        ++bounce;
+      }
+      sample_done = !scattered || bounce >= P.max_depth;
+    }
+    if (sample_done) {
+      // render: col += color(...) (main.cu:124), then the next sample of this slot, if any
+      float4 c = A.col[slot];
+      c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
+      A.col[slot] = c;
+      sample += P.substreams;
+      if (sample < P.sample_base + P.sample_count) {
+        if constexpr (MODE == RNG_PHILOX) rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
+        start_sample(S, P, A, slot, si, sample, g);
+        alive = true;
+      }
+    } else {
+      A.ray_o[slot] = make_float4(next.o.x, next.o.y, next.o.z, next.tm);
+      A.ray_d[slot] = make_float4(next.d.x, next.d.y, next.d.z, 0.f);
+      A.thr[slot] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce));
+      A.rad[slot] = make_float4(rad.x, rad.y, rad.z, __int_as_float(sample));
+      alive = true;
+    }
+    rng_store(g, A, P, slot);
+  }
+  const int np = warp_append(&C->n_active[parity ^ 1], alive);
+  if (alive) next_list[np] = slot;
+}
+
+RT_D float apply_gamma(float c, float gamma) {  // main.cu:37-42
+  if (gamma == 1.0f) return c;
+  const float inv = frcp(gamma);
+  return powf(fmaxf(c, 0.0f), inv);
+}
+
+// accum: linear sum over this rank's samples per LOCAL pixel (float3); the unit the NCCL reduce sums.
+__global__ void k_accumulate(RenderParams P, PathArrays A, float* accum) {
+  const int lpix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npl = P.rows_local * P.nx;
+  if (lpix >= npl) return;
+  float x = 0.f, y = 0.f, z = 0.f;
+  for (int s = 0; s < P.substreams; ++s) {
+    const float4 c = A.col[(size_t)s * npl + lpix];
+    x = (s == 0) ? c.x : fadd(x, c.x); y = (s == 0) ? c.y : fadd(y, c.y); z = (s == 0) ? c.z : fadd(z, c.z);
+  }
+  accum[3 * lpix + 0] = x; accum[3 * lpix + 1] = y; accum[3 * lpix + 2] = z;
+}
+
+// fb = gamma(accum / ns) (main.cu:128-132). accum/fb are indexed by local pixel.
+__global__ void k_resolve(int n_pix, int ns, float gamma, const float* accum, float* fb) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  const float k = frcp((float)ns);  // col /= float(ns): k = 1.0/t, then three multiplies (vec3.cuh:145-153)
+  fb[3 * p + 0] = apply_gamma(fmul(accum[3 * p + 0], k), gamma);
+  fb[3 * p + 1] = apply_gamma(fmul(accum[3 * p + 1], k), gamma);
+  fb[3 * p + 2] = apply_gamma(fmul(accum[3 * p + 2], k), gamma);
+}
+
+// Primary-hit AOV: centre ray of the pixel (no jitter, no lens offset, time0).
+__global__ void k_aov(DScene S, RenderParams P, int* obj, int* mat, float* tout, WaveCounters* C) {
+  const int lpix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lpix >= P.rows_local * P.nx) return;
+  const int lr = lpix / P.nx, i = lpix - lr * P.nx, j = lr * P.world + P.rank;
+  const float s = fdiv(fadd((float)i, 0.5f), (float)P.nx), t = fdiv(fadd((float)j, 0.5f), (float)P.ny);
+  Ray r;
+  r.o = S.cam.origin;
+  r.d = vsub(vmad(t, S.cam.vertical, vmad(s, S.cam.horizontal, S.cam.llc)), S.cam.origin);
+  r.tm = (float)S.cam.time0;
+  const Hit h = closest_hit(S, r, P.tmin, FLT_MAX, &C->overflow);
+  obj[lpix] = h.tlp;
+  mat[lpix] = h.tlp >= 0 ? S.tlp[h.tlp].mat : -1;
+  tout[lpix] = h.tlp >= 0 ? h.t : 0.f;
+}
+
+}  // namespace rt

@@ -1,0 +1,108 @@
+/* rt_api.h — C ABI of the B200-native render path (librt_b200.so).
+ *
+ * The reference (slbouknight/accelerated-ray-tracer) has no FFI: its "API" is one host function per
+ * scene that allocates, launches create_world_* / render_init / render and prints a PPM
+ * (main.cu:654-1322). Each entry point below replaces one stage of those host functions; the
+ * citation says which. Plain pointers and sizes only; the library owns all device memory, the
+ * caller owns every host buffer. Functions return 0 on success, non-zero on error with the message
+ * in rt_last_error() (the reference prints and exit(99)s instead, main.cu:23-35).
+ *
+ * Threading: one host thread drives one rt_scene; scenes are independent. The library never falls
+ * back to a CPU renderer: without a CUDA device rt_build_scene fails.
+ */
+#ifndef RT_API_H
+#define RT_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rt_scene rt_scene; /* opaque */
+
+/* Which generator to run and at what resolution. Replaces the hard-coded `switch (10)` and the
+ * per-scene `int nx=.., ny=..` (main.cu:1307-1322, 654-1305). */
+typedef struct rt_scene_desc {
+  int32_t scene_id;        /* 1..10 = main()'s cases: 1 bouncing, 2 checker, 3 earth, 4 perlin, 5 quads,
+                              6 simple_light, 7 cornell, 8 cornell_smoke, 9 final, 10 original */
+  int32_t nx, ny;          /* <= 0: the scene function's own resolution; nx/ny feeds the camera aspect */
+  int32_t grid_half;       /* scene 1 only: GRID_MIN/MAX (main.cu:140-141); <= 0 means 11 (488 spheres) */
+  int32_t device;          /* CUDA device ordinal; < 0: current device */
+  const char* texture_dir; /* directory with <name>.ppm (P6) textures; NULL = "textures" (main.cu:1186) */
+} rt_scene_desc;
+
+/* Replaces the arguments of render<<<>>> and the per-scene constants (main.cu:107-109, 1179, 1208). */
+typedef struct rt_render_params {
+  int32_t spp;             /* ns; <= 0: the scene function's own value */
+  int32_t max_depth;       /* <= 0: 50 (main.cu:54) */
+  float gamma;             /* <= 0: 2.2 */
+  float t_min;             /* <= 0: 0.001 (main.cu:57) */
+  float background[3];     /* used when override_background != 0, else the scene function's */
+  int32_t gradient_bg;
+  int32_t override_background;
+  uint64_t seed;           /* 0: 1984 (main.cu:92, 104) */
+  int32_t rng_mode;        /* 0 = Philox4x32-10 (counter based), 1 = reference XORWOW streams, curand_init(1984+pixel,0,0) */
+  int32_t split_mode;      /* 0 = tile split (rank owns scanlines j = rank mod world), 1 = spp split */
+  int32_t rank, world;     /* this process's share; world <= 0 means 1 */
+  int32_t substreams;      /* path slots per pixel; <= 0: automatic. Forced to 1 in reference-RNG mode */
+  int32_t aov;             /* != 0: also produce primary-hit object id / material id / t buffers */
+} rt_render_params;
+
+typedef struct rt_scene_info {
+  int32_t scene_id, nx, ny;
+  int32_t n_top, n_obj, n_mat, n_tex, n_img, n_bvh_nodes;
+  int32_t default_nx, default_ny, default_spp, gradient_bg;
+  float background[3];
+  float bvh_build_ms;      /* device time of the BVH build */
+  uint64_t h2d_bytes;      /* bytes uploaded by rt_build_scene */
+} rt_scene_info;
+
+typedef struct rt_render_stats {
+  double device_ms;        /* cudaEvent span over all render kernels (k_start .. k_resolve) */
+  uint64_t rays;           /* closest-hit queries = bounce-loop iterations of color() (main.cu:54-57) */
+  uint64_t samples;        /* camera samples rendered by this rank */
+  int32_t waves, kernel_launches;
+  int32_t rows_local, nx;  /* shape of this rank's framebuffer share */
+  int32_t substreams, n_slots;
+  uint32_t stack_overflow; /* must be 0 */
+  int32_t pad_;
+} rt_render_stats;
+
+/* create_world_*<<<1,1>>> + texture upload (main.cu:1186-1204): host generator -> H2D -> device BVH build. */
+int rt_build_scene(const rt_scene_desc* desc, rt_scene** out);
+/* render_init + render (main.cu:1207-1209). device_ms / rays may be NULL. */
+int rt_render(rt_scene* s, const rt_render_params* p, double* device_ms, uint64_t* rays);
+int rt_render_stats_get(rt_scene* s, rt_render_stats* out);
+/* The managed-memory framebuffer read (main.cu:1212-1221). rgb: rows_local*nx*3 floats, gamma applied,
+ * local row lr is image row j = lr*world + rank, j = 0 is the BOTTOM scanline like the reference's fb.
+ * obj_id / mat_id / t (each rows_local*nx, nullable) need aov != 0 in the last rt_render. */
+int rt_readback(rt_scene* s, float* rgb, int32_t* obj_id, int32_t* mat_id);
+int rt_readback_t(rt_scene* s, float* t);
+/* free_world + cudaFree (main.cu:1223-1236). */
+void rt_destroy(rt_scene* s);
+const char* rt_last_error(void);
+
+int rt_scene_info_get(rt_scene* s, rt_scene_info* out);
+/* The scene in the flat SD format of rt_scene_desc.h (for parity tests). *needed = size; copies if cap suffices.
+ * rank[] (nullable, n_top ints): position of each top-level object in the reference BVH's leaf order. */
+int rt_scene_export(rt_scene* s, void* buf, size_t cap, size_t* needed, int32_t* rank);
+/* Same, generated without a GPU (sinf/cosf/tanf from the host libm instead of libdevice: fields derived
+ * from them may differ from the GPU build in the last place). Tooling and CPU-side tests only. */
+int rt_scene_export_host(const rt_scene_desc* desc, void* buf, size_t cap, size_t* needed, int32_t* rank, int32_t rank_cap);
+
+/* Multi-GPU plumbing (spp split): the linear per-pixel radiance sums of this rank live in a device
+ * buffer of rows_local*nx*3 floats that the caller may reduce across ranks (NCCL) before resolving. */
+int rt_accum_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
+int rt_resolve(rt_scene* s, int32_t total_spp, float gamma); /* accum -> framebuffer: /ns, gamma (main.cu:128-132) */
+
+/* PPM writer of the scene functions (main.cu:1212-1221): "P3\n{nx} {ny}\n255\n", rows j = ny-1..0,
+ * int(255.99f*c) per channel, no clamp. rgb is a FULL image (ny*nx*3, row 0 = bottom). double_scale != 0
+ * reproduces bouncing_spheres' `int(255.99*c)` in double (main.cu:722-724). Returns bytes written or < 0. */
+long rt_write_ppm(const char* path /* NULL = stdout */, const float* rgb, int32_t nx, int32_t ny, int32_t double_scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_API_H */

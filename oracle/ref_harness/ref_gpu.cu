@@ -1,0 +1,261 @@
+// ref_gpu.cu — TEST/BENCH INFRASTRUCTURE (not product code).
+//
+// Host driver for the reference's OWN CUDA build recompiled for sm_100: it includes the
+// reference's device part (all headers + main.cu up to the first host function; staged by
+// oracle/build_ref.sh under /tmp with the one-line dtor fix of hittable.cuh:26 and a run-time grid
+// size for create_world_bouncing) and launches the stock kernels rand_init / create_world_* /
+// render_init / render exactly like the reference's host functions do (main.cu:654-1305), with
+// argv-selected scene, resolution and spp, cudaEvent timing around render_init+render
+// (main.cu:1207-1208), and the dumps described in ref_common.h.
+//
+// Output: one JSON line on stdout; optional <out>.sd / <out>.ids / <out>.fb files.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <iostream>
+#include <math.h>
+#include <float.h>
+#include <time.h>
+#include <curand_kernel.h>
+#include <math_constants.h>
+
+__device__ int g_grid_half = 11;  // GRID_MIN/GRID_MAX of main.cu:140-141 made run-time (C5 scale-up)
+
+#define private public
+#include REF_DEVICE_PART
+#undef private
+
+#include "ref_common.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); exit(99); } } while (0)
+
+static DeviceImage load_ppm_to_device(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); return DeviceImage{}; }
+  int w = 0, h = 0, mx = 0;
+  if (fscanf(f, "P6 %d %d %d", &w, &h, &mx) != 3) { fclose(f); return DeviceImage{}; }
+  fgetc(f);
+  std::vector<unsigned char> px((size_t)w * h * 3);
+  size_t got = fread(px.data(), 1, px.size(), f);
+  fclose(f);
+  if (got != px.size()) return DeviceImage{};
+  unsigned char* d = nullptr;
+  CK(cudaMalloc(&d, px.size()));
+  CK(cudaMemcpy(d, px.data(), px.size(), cudaMemcpyHostToDevice));
+  return DeviceImage{d, w, h, 3};
+}
+
+__global__ void k_set_grid(int g) { g_grid_half = g; }
+__global__ void k_probe(RefVptrs* vp) { rh_probe_vptrs(vp); }
+__global__ void k_export(RefExport* E, hittable** d_list, int n_top, hittable** world, camera** cam,
+                         rt_camera_desc* cam_out, int* leaf_mismatch) {
+  rh_export_scene(*E, d_list, n_top);
+  rh_export_camera(cam_out, *cam);
+  // check d_list order == in-order leaf walk of the BVH
+  const hittable** leaves = (const hittable**)malloc(sizeof(void*) * (n_top + 1));
+  int n = 0;
+  rh_leaf_order(E->vp, *world, leaves, &n);
+  int bad = (n != n_top);
+  for (int k = 0; k < n_top && k < n; ++k) bad += (leaves[k] != d_list[k]);
+  *leaf_mismatch = bad;
+  free(leaves);
+}
+__global__ void k_ids(const RefExport* E, hittable** d_list, int n_top, hittable** world, camera** cam,
+                      int nx, int ny, RefIds out) {
+  int i = threadIdx.x + blockIdx.x * blockDim.x;
+  int j = threadIdx.y + blockIdx.y * blockDim.y;
+  if (i >= nx || j >= ny) return;
+  rh_primary_ids(*E, d_list, n_top, world, *cam, i, j, nx, ny, out);
+}
+__global__ void k_render_counted(vec3* fb, int nx, int ny, int ns, float gamma, camera** cam, hittable** world,
+                                 vec3 background, int use_gradient_bg, unsigned long long* rays) {
+  int i = threadIdx.x + blockIdx.x * blockDim.x;
+  int j = threadIdx.y + blockIdx.y * blockDim.y;
+  if (i >= nx || j >= ny) return;
+  unsigned long long r = 0;
+  fb[j * nx + i] = rh_render_pixel_counted(i, j, nx, ny, ns, gamma, cam, world, background, use_gradient_bg, r);
+  atomicAdd(rays, r);
+}
+
+template <class T> static T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc(&p, n * sizeof(T))); CK(cudaMemset(p, 0, n * sizeof(T))); return p; }
+template <class T> static std::vector<T> dget(const T* d, size_t n) { std::vector<T> h(n); CK(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost)); return h; }
+
+int main(int argc, char** argv) {
+  RhArgs a;
+  for (int i = 1; i < argc; ++i) {
+    std::string s = argv[i];
+    auto nxt = [&]() { return i + 1 < argc ? argv[++i] : (char*)"0"; };
+    if (s == "--scene") a.scene = atoi(nxt());
+    else if (s == "--nx") a.nx = atoi(nxt());
+    else if (s == "--ny") a.ny = atoi(nxt());
+    else if (s == "--ns") a.ns = atoi(nxt());
+    else if (s == "--reps") a.reps = atoi(nxt());
+    else if (s == "--grid") a.grid_half = atoi(nxt());
+    else if (s == "--ids") a.ids = atoi(nxt());
+    else if (s == "--count") a.count = atoi(nxt());
+    else if (s == "--textures") a.tex_dir = nxt();
+    else if (s == "--out") a.out = nxt();
+    else { fprintf(stderr, "unknown arg %s\n", s.c_str()); return 2; }
+  }
+  RhSceneParams sp = rh_scene_params(a.scene, a.grid_half);
+  if (sp.nx == 0) { fprintf(stderr, "bad scene\n"); return 2; }
+  const int nx = a.nx > 0 ? a.nx : sp.nx, ny = a.ny > 0 ? a.ny : sp.ny, ns = a.ns;
+  const float gamma = 2.2f;
+
+  // limits as in final_scene / cornell_smoke (main.cu:1132-1133, 1181-1182), enlarged for C5
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, 65536));
+  CK(cudaDeviceSetLimit(cudaLimitMallocHeapSize, (size_t)1024 * 1024 * 1024));
+
+  std::string td = a.tex_dir;
+  DeviceImage earth{}, ball{};
+  if (a.scene == 3 || a.scene == 9) earth = load_ppm_to_device(td + "/earthmap.ppm");
+  if (a.scene == 6) ball = load_ppm_to_device(td + "/poolball.ppm");
+  if (a.scene == 10) { earth = load_ppm_to_device(td + "/porcelain.ppm"); ball = load_ppm_to_device(td + "/8ball.ppm"); }
+  if ((a.scene == 3 || a.scene == 9 || a.scene == 10) && !earth.valid()) { fprintf(stderr, "texture missing\n"); return 3; }
+
+  const int num_pixels = nx * ny;
+  vec3* fb = dalloc<vec3>(num_pixels);
+  curandState* d_rand_state = dalloc<curandState>(num_pixels);
+  curandState* d_rand_state2 = dalloc<curandState>(1);
+  rand_init<<<1, 1>>>(d_rand_state2);
+  CK(cudaGetLastError());
+
+  camera** d_camera = dalloc<camera*>(1);
+  hittable** d_world = dalloc<hittable*>(1);
+  const int n_list = sp.n_list;
+  hittable** d_list = dalloc<hittable*>(n_list + 8);
+  k_set_grid<<<1, 1>>>(a.grid_half);
+
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  switch (a.scene) {
+    case 1: create_world_bouncing<<<1, 1>>>(d_list, d_world, d_camera, nx, ny, d_rand_state2); break;
+    case 2: create_world_checker<<<1, 1>>>(d_list, d_world, d_camera, nx, ny, d_rand_state2); break;
+    case 3: create_world_earth<<<1, 1>>>(d_list, d_world, d_camera, nx, ny, earth); break;
+    case 4: create_world_perlin<<<1, 1>>>(d_list, d_world, d_camera, nx, ny, 4.0f); break;
+    case 5: create_world_quads<<<1, 1>>>(d_list, d_world, d_camera, nx, ny); break;
+    case 6: create_world_simple_light<<<1, 1>>>(d_list, d_world, d_camera, nx, ny, ball); break;
+    case 7: create_world_cornell<<<1, 1>>>(d_list, d_world, d_camera, nx, ny); break;
+    case 8: create_world_cornell_smoke<<<1, 1>>>(d_list, d_world, d_camera, nx, ny); break;
+    case 9: create_world_final<<<1, 1>>>(d_list, d_world, d_camera, nx, ny, earth); break;
+    case 10: create_world_original<<<1, 1>>>(d_list, d_world, d_camera, nx, ny, earth, ball); break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float build_ms = 0; CK(cudaEventElapsedTime(&build_ms, e0, e1));
+
+  // ---- export ----
+  RefVptrs* d_vp = dalloc<RefVptrs>(1);
+  k_probe<<<1, 1>>>(d_vp);
+  CK(cudaDeviceSynchronize());
+  const int cap_obj = n_list * 8 + 64, cap_mat = n_list + 64, cap_tex = n_list * 2 + 64, cap_img = 8;
+  RefExport E{};
+  E.vp = d_vp;
+  E.tex = dalloc<rt_texture_desc>(cap_tex); E.tex_ptr = dalloc<const void*>(cap_tex); E.cap_tex = cap_tex;
+  E.mat = dalloc<rt_material_desc>(cap_mat); E.mat_ptr = dalloc<const void*>(cap_mat); E.cap_mat = cap_mat;
+  E.obj = dalloc<rt_object_desc>(cap_obj); E.cap_obj = cap_obj;
+  E.img = dalloc<rt_image_desc>(cap_img); E.img_ptr = dalloc<const void*>(cap_img); E.cap_img = cap_img;
+  E.top = dalloc<int>(n_list + 8);
+  RefExport* d_E = dalloc<RefExport>(1);
+  CK(cudaMemcpy(d_E, &E, sizeof(E), cudaMemcpyHostToDevice));
+  rt_camera_desc* d_cam = dalloc<rt_camera_desc>(1);
+  int* d_leaf_bad = dalloc<int>(1);
+  k_export<<<1, 1>>>(d_E, d_list, n_list, d_world, d_camera, d_cam, d_leaf_bad);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  RefExport hE = dget(d_E, 1)[0];
+  int leaf_bad = dget(d_leaf_bad, 1)[0];
+  if (a.out) {
+    rt_sd_header h{};
+    h.magic = RT_SD_MAGIC; h.scene_id = a.scene; h.nx = nx; h.ny = ny;
+    h.n_tex = hE.n_tex; h.n_mat = hE.n_mat; h.n_obj = hE.n_obj; h.n_top = hE.n_top; h.n_img = hE.n_img;
+    h.cam = dget(d_cam, 1)[0];
+    std::string p = std::string(a.out) + ".sd";
+    FILE* f = fopen(p.c_str(), "wb");
+    fwrite(&h, sizeof(h), 1, f);
+    auto t = dget(hE.tex, hE.n_tex); fwrite(t.data(), sizeof(rt_texture_desc), t.size(), f);
+    auto m = dget(hE.mat, hE.n_mat); fwrite(m.data(), sizeof(rt_material_desc), m.size(), f);
+    auto o = dget(hE.obj, hE.n_obj); fwrite(o.data(), sizeof(rt_object_desc), o.size(), f);
+    auto tp = dget(hE.top, hE.n_top); fwrite(tp.data(), sizeof(int), tp.size(), f);
+    auto im = dget(hE.img, hE.n_img); fwrite(im.data(), sizeof(rt_image_desc), im.size(), f);
+    fclose(f);
+  }
+
+  dim3 threads(8, 8), blocks(nx / 8 + 1, ny / 8 + 1);  // main.cu:702-703
+  const vec3 bg(sp.bg[0], sp.bg[1], sp.bg[2]);
+
+  // ---- primary-hit AOV ----
+  int id_mismatch = -1;
+  if (a.ids && a.out) {
+    RefIds R{dalloc<int>(num_pixels), dalloc<float>(num_pixels), dalloc<int>(num_pixels), dalloc<float>(num_pixels)};
+    k_ids<<<blocks, threads>>>(d_E, d_list, n_list, d_world, d_camera, nx, ny, R);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    auto obj = dget(R.obj, num_pixels); auto t = dget(R.t, num_pixels);
+    auto mat = dget(R.mat, num_pixels); auto bt = dget(R.bvh_t, num_pixels);
+    id_mismatch = 0;
+    for (int k = 0; k < num_pixels; ++k) id_mismatch += (memcmp(&t[k], &bt[k], 4) != 0);
+    std::string p = std::string(a.out) + ".ids";
+    FILE* f = fopen(p.c_str(), "wb");
+    int hdr[2] = {nx, ny}; fwrite(hdr, sizeof(int), 2, f);
+    fwrite(obj.data(), 4, num_pixels, f); fwrite(t.data(), 4, num_pixels, f);
+    fwrite(mat.data(), 4, num_pixels, f); fwrite(bt.data(), 4, num_pixels, f);
+    fclose(f);
+  }
+
+  // ---- stock render, timed like main.cu:699-712 but with events ----
+  float best_ms = 1e30f, sum_ms = 0;
+  for (int rep = 0; rep < a.reps; ++rep) {
+    CK(cudaEventRecord(e0));
+    render_init<<<blocks, threads>>>(nx, ny, d_rand_state);
+    render<<<blocks, threads>>>(fb, nx, ny, ns, gamma, d_camera, d_world, d_rand_state, bg, sp.gradient);
+    CK(cudaEventRecord(e1));
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    sum_ms += ms; if (ms < best_ms) best_ms = ms;
+  }
+  std::vector<vec3> h_fb = dget(fb, num_pixels);
+  if (a.out && a.reps > 0) {
+    std::string p = std::string(a.out) + ".fb";
+    FILE* f = fopen(p.c_str(), "wb");
+    int hdr[3] = {nx, ny, ns}; fwrite(hdr, sizeof(int), 3, f);
+    fwrite(h_fb.data(), sizeof(vec3), num_pixels, f);
+    fclose(f);
+  }
+
+  // ---- ray count (mirror kernel, checked against the stock output) ----
+  unsigned long long rays = 0; long long fb_mismatch = -1;
+  if (a.count) {
+    vec3* fb2 = dalloc<vec3>(num_pixels);
+    unsigned long long* d_rays = dalloc<unsigned long long>(1);
+    k_render_counted<<<blocks, threads>>>(fb2, nx, ny, ns, gamma, d_camera, d_world, bg, sp.gradient, d_rays);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    rays = dget(d_rays, 1)[0];
+    if (a.reps > 0) {
+      auto h2 = dget(fb2, num_pixels);
+      fb_mismatch = 0;
+      for (int k = 0; k < num_pixels; ++k) fb_mismatch += (memcmp(&h2[k], &h_fb[k], sizeof(vec3)) != 0);
+    }
+  }
+
+  const double samples = (double)num_pixels * ns;
+  const double mean_ms = a.reps > 0 ? sum_ms / a.reps : 0.0;
+  printf("{\"impl\": \"reference-cuda-sm100\", \"scene\": %d, \"name\": \"%s\", \"nx\": %d, \"ny\": %d, \"ns\": %d, "
+         "\"grid_half\": %d, \"n_top\": %d, \"n_obj\": %d, \"n_mat\": %d, \"n_tex\": %d, \"export_error\": %d, "
+         "\"leaf_order_mismatch\": %d, \"id_t_mismatch\": %d, \"build_ms\": %.3f, \"render_ms_best\": %.4f, "
+         "\"render_ms_mean\": %.4f, \"reps\": %d, \"rays\": %llu, \"samples\": %.0f, \"rays_per_sample\": %.4f, "
+         "\"counted_fb_mismatch\": %lld, \"mrays_per_s\": %.3f, \"msamples_per_s\": %.3f}\n",
+         a.scene, sp.name, nx, ny, ns, a.grid_half, hE.n_top, hE.n_obj, hE.n_mat, hE.n_tex, hE.error, leaf_bad,
+         id_mismatch, build_ms, a.reps > 0 ? best_ms : 0.f, mean_ms, a.reps, rays, samples, rays / samples,
+         fb_mismatch, mean_ms > 0 ? rays / (mean_ms * 1e3) : 0.0, mean_ms > 0 ? samples / (mean_ms * 1e3) : 0.0);
+  fflush(stdout);
+  cudaDeviceReset();
+  return 0;
+}
