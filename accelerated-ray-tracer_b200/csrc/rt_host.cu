@@ -166,8 +166,12 @@ static int upload_scene(rt_scene* s) {
   for (int k = 0; k < n; ++k) {
     const rt_object_desc& o = sd.obj[sd.top[k]];
     tlp[k].ref = F.flatten(sd.top[k]);
-    tlp[k].mat = o.mat;
-    tlp[k].queue = queue_of(sd.mat[o.mat].kind);
+    int mid = sd.top[k];  // instance wrappers carry no material of their own: take the wrapped object's
+    while (sd.obj[mid].kind == RT_OBJ_TRANSLATE || sd.obj[mid].kind == RT_OBJ_ROTATE_Y) mid = sd.obj[mid].child;
+    const int mat = sd.obj[mid].mat;
+    if (mat < 0 || mat >= (int)sd.mat.size()) return fail("upload_scene: top-level object without a material");
+    tlp[k].mat = mat;
+    tlp[k].queue = queue_of(sd.mat[mat].kind);
     tlp[k].rank = s->rank[k];
     refs[k] = tlp[k].ref;
     for (int a = 0; a < 3; ++a) { boxes[k].mn[a] = o.box_min[a]; boxes[k].mx[a] = o.box_max[a]; }
@@ -401,7 +405,8 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   CU(cudaMemsetAsync(s->counters.p, 0, sizeof(WaveCounters), st));
   CU(cudaEventRecord(e0, st));
   const int B = 128;
-  int launches = 0, waves = 0;
+  int launches = 0, waves = 0, prof_waves = 0;
+  double prof_trace_ms = 0.0, prof_shade_ms = 0.0;
   if (P.n_slots > 0 && P.sample_count > 0) {
     const int G = (P.n_slots + B - 1) / B;
     if (ref_rng) k_start<RNG_REFERENCE><<<G, B, 0, st>>>(s->dscene, P, A, s->list0.p, s->counters.p);
@@ -411,22 +416,36 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     int batch = 8;
     if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
     int parity = 0;
+    std::vector<cudaEvent_t> pev;
+    if (p->profile) { pev.resize(3 * batch); for (auto& e : pev) CU(cudaEventCreate(&e)); }
     while (bound > 0) {
       for (int w = 0; w < batch; ++w) {
         const int Gt = (bound + B - 1) / B;
         const int Gs = (bound + 32 * Q_COUNT + B - 1) / B;
         int* cur = parity ? s->list1.p : s->list0.p;
         int* nxt = parity ? s->list0.p : s->list1.p;
+        if (p->profile) CU(cudaEventRecord(pev[3 * w], st));
         k_trace<<<Gt, B, 0, st>>>(s->dscene, P, A, cur, s->queues.p, s->counters.p, parity);
+        if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], st));
         if (ref_rng) k_shade<RNG_REFERENCE><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, nxt, s->counters.p, parity);
         else k_shade<RNG_PHILOX><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, nxt, s->counters.p, parity);
+        if (p->profile) CU(cudaEventRecord(pev[3 * w + 2], st));
         parity ^= 1; launches += 2; ++waves;
       }
       CU(cudaMemcpyAsync(s->h_counters, s->counters.p, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
       CU(cudaEventRecord(ev, st));
       CU(cudaEventSynchronize(ev));
+      if (p->profile) {
+        for (int w = 0; w < batch; ++w) {
+          float a = 0.f, b = 0.f;
+          CU(cudaEventElapsedTime(&a, pev[3 * w], pev[3 * w + 1]));
+          CU(cudaEventElapsedTime(&b, pev[3 * w + 1], pev[3 * w + 2]));
+          prof_trace_ms += a; prof_shade_ms += b; ++prof_waves;
+        }
+      }
       bound = s->h_counters->n_active[parity];
     }
+    for (auto& e : pev) cudaEventDestroy(e);
   }
   {
     const int Gp = (int)((n_pix + 255) / 256);
@@ -452,6 +471,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   R.device_ms = ms; R.rays = s->h_counters->rays; R.samples = (uint64_t)n_pix * (uint64_t)P.sample_count;
   R.waves = waves; R.kernel_launches = launches; R.rows_local = P.rows_local; R.nx = P.nx;
   R.substreams = S; R.n_slots = P.n_slots; R.stack_overflow = s->h_counters->overflow;
+  R.profiled_waves = prof_waves; R.trace_ms = prof_trace_ms; R.shade_ms = prof_shade_ms;
   if (device_ms) *device_ms = ms;
   if (rays) *rays = R.rays;
   if (R.stack_overflow) return fail("rt_render: BVH traversal stack overflow (RT_STACK too small for this scene)");
@@ -489,6 +509,12 @@ extern "C" int rt_readback_t(rt_scene* s, float* t) {
 extern "C" int rt_accum_device_ptr(rt_scene* s, void** dptr, size_t* n_floats) {
   if (!s || !dptr) return fail("rt_accum_device_ptr: null argument");
   *dptr = s->accum.p;
+  if (n_floats) *n_floats = (size_t)s->last.rows_local * s->last.nx * 3;
+  return 0;
+}
+extern "C" int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats) {
+  if (!s || !dptr) return fail("rt_fb_device_ptr: null argument");
+  *dptr = s->fb.p;
   if (n_floats) *n_floats = (size_t)s->last.rows_local * s->last.nx * 3;
   return 0;
 }

@@ -127,7 +127,8 @@ RT_D V3 texture_value(const DScene& S, int tex, float u, float v, V3 p) {
         float q = smoothstep_(0.75f, 0.98f, stripes);
         V3 cG = v3(t.p[10], t.p[11], t.p[12]), cN = v3(t.p[7], t.p[8], t.p[9]);
         float omq = fsub(1.f, q);
-        return v3(ffma(omq, cG.x, fmul(q, cN.x)), ffma(omq, cG.y, fmul(q, cN.y)), ffma(omq, cG.z, fmul(q, cN.z)));
+        // (1-t)*cG + t*cN: the reference SASS fuses the RIGHT product here: fma(t, cN, (1-t)*cG)
+        return v3(ffma(q, cN.x, fmul(omq, cG.x)), ffma(q, cN.y, fmul(omq, cG.y)), ffma(q, cN.z, fmul(omq, cG.z)));
       }
       case T_FELT: {  // texture.cuh:125-147
         float m = perlin_noise(vscale(t.p[0], p));

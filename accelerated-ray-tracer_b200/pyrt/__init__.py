@@ -33,7 +33,7 @@ class RenderParamsC(C.Structure):
     _fields_ = [("spp", C.c_int32), ("max_depth", C.c_int32), ("gamma", C.c_float), ("t_min", C.c_float),
                 ("background", C.c_float * 3), ("gradient_bg", C.c_int32), ("override_background", C.c_int32),
                 ("seed", C.c_uint64), ("rng_mode", C.c_int32), ("split_mode", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("substreams", C.c_int32), ("aov", C.c_int32)]
+                ("world", C.c_int32), ("substreams", C.c_int32), ("aov", C.c_int32), ("profile", C.c_int32)]
 
 
 class SceneInfoC(C.Structure):
@@ -47,12 +47,13 @@ class SceneInfoC(C.Structure):
 class RenderStatsC(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("rays", C.c_uint64), ("samples", C.c_uint64), ("waves", C.c_int32),
                 ("kernel_launches", C.c_int32), ("rows_local", C.c_int32), ("nx", C.c_int32),
-                ("substreams", C.c_int32), ("n_slots", C.c_int32), ("stack_overflow", C.c_uint32), ("pad_", C.c_int32)]
+                ("substreams", C.c_int32), ("n_slots", C.c_int32), ("stack_overflow", C.c_uint32),
+                ("profiled_waves", C.c_int32), ("trace_ms", C.c_double), ("shade_ms", C.c_double)]
 
 
 EXPORTS = ["rt_build_scene", "rt_render", "rt_render_stats_get", "rt_readback", "rt_readback_t", "rt_destroy",
            "rt_last_error", "rt_scene_info_get", "rt_scene_export", "rt_scene_export_host", "rt_accum_device_ptr",
-           "rt_resolve", "rt_write_ppm"]
+           "rt_resolve", "rt_fb_device_ptr", "rt_write_ppm"]
 
 _lib = None
 
@@ -79,6 +80,7 @@ def lib():
                                            C.c_void_p, C.c_int32]
         L.rt_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.rt_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_float]
+        L.rt_fb_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.rt_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.rt_write_ppm.restype = C.c_long
         _lib = L
@@ -266,7 +268,7 @@ class Scene:
         self.close()
 
     def render(self, spp=0, rng_mode=0, rank=0, world=1, split_mode=0, substreams=0, aov=False, seed=0,
-               max_depth=0, gamma=0.0, background=None, gradient_bg=None):
+               max_depth=0, gamma=0.0, background=None, gradient_bg=None, profile=False):
         p = RenderParamsC()
         p.spp, p.max_depth, p.gamma, p.t_min = spp, max_depth, gamma, 0.0
         if background is not None:
@@ -274,7 +276,7 @@ class Scene:
             p.background[0], p.background[1], p.background[2] = background
             p.gradient_bg = int(bool(gradient_bg))
         p.seed, p.rng_mode, p.split_mode, p.rank, p.world = seed, rng_mode, split_mode, rank, world
-        p.substreams, p.aov = substreams, int(bool(aov))
+        p.substreams, p.aov, p.profile = substreams, int(bool(aov)), int(bool(profile))
         ms, rays = C.c_double(0), C.c_uint64(0)
         _check(lib().rt_render(self._h, C.byref(p), C.byref(ms), C.byref(rays)))
         st = RenderStatsC()
@@ -302,6 +304,11 @@ class Scene:
     def accum_ptr(self):
         p, n = C.c_void_p(), C.c_size_t(0)
         _check(lib().rt_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def fb_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        _check(lib().rt_fb_device_ptr(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
     def resolve(self, total_spp=0, gamma=0.0):
@@ -341,3 +348,12 @@ def write_ppm(path, fb, double_scale=False):
     if n < 0:
         raise RtError(lib().rt_last_error().decode())
     return n
+
+
+class DevicePtrView:
+    """Zero-copy view of library-owned device memory for torch (torch.as_tensor(view, device="cuda")).
+    Plumbing for the NCCL reduce / gather of torch.distributed; no compute happens in torch."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}

@@ -48,6 +48,7 @@ typedef struct rt_render_params {
   int32_t rank, world;     /* this process's share; world <= 0 means 1 */
   int32_t substreams;      /* path slots per pixel; <= 0: automatic. Forced to 1 in reference-RNG mode */
   int32_t aov;             /* != 0: also produce primary-hit object id / material id / t buffers */
+  int32_t profile;         /* != 0: CUDA events around every k_trace / k_shade launch (rt_render_stats.trace_ms / shade_ms) */
 } rt_render_params;
 
 typedef struct rt_scene_info {
@@ -67,7 +68,8 @@ typedef struct rt_render_stats {
   int32_t rows_local, nx;  /* shape of this rank's framebuffer share */
   int32_t substreams, n_slots;
   uint32_t stack_overflow; /* must be 0 */
-  int32_t pad_;
+  int32_t profiled_waves;  /* waves covered by trace_ms / shade_ms (profile != 0) */
+  double trace_ms, shade_ms; /* summed device time of the k_trace / k_shade launches */
 } rt_render_stats;
 
 /* create_world_*<<<1,1>>> + texture upload (main.cu:1186-1204): host generator -> H2D -> device BVH build. */
@@ -96,6 +98,8 @@ int rt_scene_export_host(const rt_scene_desc* desc, void* buf, size_t cap, size_
  * buffer of rows_local*nx*3 floats that the caller may reduce across ranks (NCCL) before resolving. */
 int rt_accum_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
 int rt_resolve(rt_scene* s, int32_t total_spp, float gamma); /* accum -> framebuffer: /ns, gamma (main.cu:128-132) */
+/* Device address of this rank's framebuffer share (rows_local*nx*3 floats), e.g. for an NCCL gather of tiles. */
+int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
 
 /* PPM writer of the scene functions (main.cu:1212-1221): "P3\n{nx} {ny}\n255\n", rows j = ny-1..0,
  * int(255.99f*c) per channel, no clamp. rgb is a FULL image (ny*nx*3, row 0 = bottom). double_scale != 0
