@@ -76,7 +76,7 @@ struct rt_scene {
   DBuf<WaveCounters> counters;
   WaveCounters* h_counters = nullptr;  // pinned
   DBuf<float> accum, fb, aov_t; DBuf<int> aov_obj, aov_mat;
-  size_t slots_cap = 0, pix_cap = 0;
+  size_t slots_cap = 0, pix_cap = 0, accum_valid_pix = 0;
   RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
   ~rt_scene() {
     for (auto p : image_px) cudaFree(p);
@@ -350,7 +350,7 @@ static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rn
   if (n_pix > s->pix_cap) {
     CU(s->accum.alloc(3 * n_pix)); CU(s->fb.alloc(3 * n_pix));
     s->aov_obj.free(); s->aov_mat.free(); s->aov_t.free();
-    s->pix_cap = n_pix;
+    s->pix_cap = n_pix; s->accum_valid_pix = 0;
   }
   if (aov && s->aov_obj.n < n_pix) { CU(s->aov_obj.alloc(s->pix_cap)); CU(s->aov_mat.alloc(s->pix_cap)); CU(s->aov_t.alloc(s->pix_cap)); }
   if (!s->counters.p) CU(s->counters.alloc(1));
@@ -415,6 +415,8 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     int bound = P.n_slots;  // the live-ray count never grows: the last known value bounds the grid
     int batch = 8;
     if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
+    FILE* wlog = nullptr;  // diagnostics: one line per wave (live rays at batch start, k_trace ms, k_shade ms)
+    if (p->profile) if (const char* e = getenv("RT_WAVE_LOG")) { wlog = fopen(e, "a"); batch = 1; }
     int parity = 0;
     std::vector<cudaEvent_t> pev;
     if (p->profile) { pev.resize(3 * batch); for (auto& e : pev) CU(cudaEventCreate(&e)); }
@@ -441,16 +443,19 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
           CU(cudaEventElapsedTime(&a, pev[3 * w], pev[3 * w + 1]));
           CU(cudaEventElapsedTime(&b, pev[3 * w + 1], pev[3 * w + 2]));
           prof_trace_ms += a; prof_shade_ms += b; ++prof_waves;
+          if (wlog) fprintf(wlog, "%d %d %.4f %.4f\n", prof_waves, bound, a, b);
         }
       }
       bound = s->h_counters->n_active[parity];
     }
     for (auto& e : pev) cudaEventDestroy(e);
+    if (wlog) fclose(wlog);
   }
   {
     const int Gp = (int)((n_pix + 255) / 256);
     if (n_pix > 0) {
-      k_accumulate<<<Gp, 256, 0, st>>>(P, A, s->accum.p);
+      k_accumulate<<<Gp, 256, 0, st>>>(P, A, s->accum.p, (p->accumulate != 0 && s->accum_valid_pix == n_pix) ? 1 : 0);
+      s->accum_valid_pix = n_pix;
       k_resolve<<<Gp, 256, 0, st>>>((int)n_pix, spp_total, gamma, s->accum.p, s->fb.p);
       launches += 2;
     }

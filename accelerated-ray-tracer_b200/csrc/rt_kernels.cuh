@@ -264,7 +264,8 @@ RT_D float apply_gamma(float c, float gamma) {  // main.cu:37-42
 }
 
 // accum: linear sum over this rank's samples per LOCAL pixel (float3); the unit the NCCL reduce sums.
-__global__ void k_accumulate(RenderParams P, PathArrays A, float* accum) {
+// add != 0: progressive pass, accum += this pass (rt_render_params.accumulate).
+__global__ void k_accumulate(RenderParams P, PathArrays A, float* accum, int add) {
   const int lpix = blockIdx.x * blockDim.x + threadIdx.x;
   const int npl = P.rows_local * P.nx;
   if (lpix >= npl) return;
@@ -273,6 +274,7 @@ __global__ void k_accumulate(RenderParams P, PathArrays A, float* accum) {
     const float4 c = A.col[(size_t)s * npl + lpix];
     x = (s == 0) ? c.x : fadd(x, c.x); y = (s == 0) ? c.y : fadd(y, c.y); z = (s == 0) ? c.z : fadd(z, c.z);
   }
+  if (add) { x = fadd(accum[3 * lpix + 0], x); y = fadd(accum[3 * lpix + 1], y); z = fadd(accum[3 * lpix + 2], z); }
   accum[3 * lpix + 0] = x; accum[3 * lpix + 1] = y; accum[3 * lpix + 2] = z;
 }
 

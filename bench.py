@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py — the headline benchmark of the render path: Mrays/s (all bounces, device-timed) on the
+Book-2 final scene (create_world_final, main.cu:498-562) at 800x800, on N B200s of one box.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                  (N > 1: launched by torchrun)
+  python bench.py --impl reference ...      the reference's own render code on the box's host cores
+
+A *step* is one progressive pass of --spp-per-step samples per pixel (default 1000) over the whole
+800x800 image on every GPU; steps use disjoint sample numbers, so the default K = 10 steps ARE the
+reference's 10000-spp final_scene() (main.cu:1179) at N = 1. At N > 1 every GPU renders its own
+--spp-per-step share per step (weak scaling: per-GPU work fixed, N x the samples per step) and the
+linear-radiance sums are reduced to rank 0 with one NCCL reduce per step, inside the timed region.
+
+value    whole-job Mrays/s with the scene resident in HBM: rays of all ranks / (max-over-ranks CUDA-event
+         span of the K steps, barrier + synchronize on both sides).
+e2e      the same metric through the C ABI with host buffers: every step is rt_build_scene (host generator,
+         H2D of scene + texture, device BVH build) + rt_render + rt_readback of the float framebuffer to host
+         + rt_destroy — what the reference's final_scene() does between process start and the PPM loop.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "accelerated-ray-tracer_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+METRIC = "Mrays/s (all bounces, device-timed) on Book-2 final scene"
+UNIT = "Mrays/s"
+SCENE_ID, NX, NY = 9, 800, 800
+# SURVEY.md §8(d) / BASELINE.md §3: work per ray of the reference algorithm on C4 (fixed normaliser)
+C4_FLOP_PER_RAY = 1685.0
+C4_BYTES_PER_RAY = 2535.0
+# k_trace's share of it: BVH nodes + primitives + media (1715 + 245 + 368 + 47) + ray read 32 + hit write 16
+C4_TRACE_BYTES_PER_RAY = 2423.0
+REF_CPU = os.path.join(ROOT, "oracle", "_ref", "ref_cpu")
+REF_GPU = os.path.join(ROOT, "baseline", "_ref", "ref_gpu")
+TEXDIRS = [os.path.join(ROOT, "oracle", "_ref", "textures"), os.path.join(ROOT, "tests", "golden", "textures")]
+
+
+def texture_dir():
+    for d in TEXDIRS:
+        if os.path.exists(os.path.join(d, "earthmap.ppm")):
+            return d
+    raise SystemExit("bench: earthmap.ppm not found (run __graft_entry__.build() where /root/reference exists)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi-equivalent clock/throttle sampling (NVML) during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def run_json(cmd, timeout):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    for line in r.stdout.splitlines()[::-1]:
+        line = line.strip()
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("no JSON from %s: rc=%d %s" % (cmd[0], r.returncode, r.stderr[-500:]))
+
+
+def cpu_reference_run(nx, ny, ns, threads, count=1):
+    """The reference's own render()/color() (compiled for the host behind oracle/shim) on this box's cores."""
+    cmd = [REF_CPU, "--scene", str(SCENE_ID), "--nx", str(nx), "--ny", str(ny), "--ns", str(ns), "--reps", "1",
+           "--count", str(count), "--threads", str(threads), "--textures", texture_dir()]
+    return run_json(cmd, 900)
+
+
+def cpu_sample_plan(threads, target_s):
+    """Bounded sample of the workload: the full 800x800 image at the spp that takes ~target_s on this box."""
+    probe = cpu_reference_run(200, 200, 1, threads)
+    per_sample_ms = probe["render_ms_mean"] / (200 * 200)
+    ns = int(max(1, min(64, round(target_s * 1e3 / (per_sample_ms * NX * NY)))))
+    return ns, probe["rays_per_sample"]
+
+
+def reference_arm(args):
+    """--impl reference: rank 0 only. kind 'reference' = /root/reference's render path compiled unmodified for
+    the host (oracle/build_ref.sh); the reference ships no CPU path of its own."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if not os.path.exists(REF_CPU):
+        raise SystemExit("bench --impl reference: oracle/_ref/ref_cpu not built")
+    threads = os.cpu_count() or 1
+    ns, _ = cpu_sample_plan(threads, 2.0)
+    res = []
+    for i in range(args.warmup + args.steps):
+        o = cpu_reference_run(NX, NY, ns, threads)
+        if i >= args.warmup:
+            res.append(o)
+    rays = sum(o["rays"] for o in res)
+    ms = sum(o["render_ms_mean"] for o in res)
+    v = rays / ms / 1e3
+    sample = "%dx%d x %d spp per step (of the 10000-spp config; throughput is linear in spp)" % (NX, NY, ns)
+    line = {"metric": METRIC, "value": round(v, 4), "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / max(len(res), 1), 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Book-2 final scene (create_world_final) 800x800, depth 50; " + sample,
+                       "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": ns},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference render()/color() compiled unmodified for the host behind oracle/shim (g++ -O2 -fopenmp, "
+                    "glibc libm); the reference's CUDA build on this GPU is reported by the default arm as reference_cuda_sm100"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def reference_cuda_run(ns=8):
+    """The reference's own CUDA build recompiled for sm_100 (baseline/_ref/ref_gpu), same scene, on this GPU."""
+    if not os.path.exists(REF_GPU):
+        return None
+    try:
+        o = run_json([REF_GPU, "--scene", str(SCENE_ID), "--nx", str(NX), "--ny", str(NY), "--ns", str(ns), "--reps", "1",
+                      "--count", "1", "--textures", texture_dir()], 600)
+        return {"value": o["mrays_per_s"], "unit": UNIT, "msamples_per_s": o["msamples_per_s"],
+                "sample": "%dx%d x %d spp, render_init+render device-timed" % (NX, NY, ns),
+                "rays_per_sample": o["rays_per_sample"], "scene_build_ms": o["build_ms"],
+                "what": "reference render kernel (main.cu:107-133) compiled unmodified, nvcc -arch=sm_100 -O3"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:200]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true",
+                    help="no per-launch CUDA events inside the timed region (roofline from one extra profiled step)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import pyrt
+    from pyrt import dist as rdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench: no CUDA device (the render path has no CPU fallback)")
+    world, rank, local = rdist.init_process_group("nccl")
+    if world != args.gpus:
+        raise SystemExit("bench: --gpus %d but WORLD_SIZE=%d (launch N>1 with torchrun)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    import torch.distributed as tdist
+    dev = torch.device("cuda", local)
+    S, K, W = args.spp_per_step, args.steps, args.warmup
+    tex = texture_dir()
+
+    def barrier():
+        if world > 1:
+            tdist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    sc = pyrt.Scene(SCENE_ID, NX, NY, texture_dir=tex, device=local)
+    passes = (W + K) * world  # every (step, rank) renders a disjoint block of S sample numbers
+    spp_all = S * passes
+
+    def step(i, profile=False):
+        st = sc.render(spp=spp_all, rng_mode=0, split_mode=1, rank=i * world + rank, world=passes, profile=profile)
+        if world > 1:
+            rdist.reduce_sum_to_root(rdist.accum_tensor(sc))  # NCCL reduce over NVLink: the image of this pass on rank 0
+        return st
+
+    for i in range(W):
+        step(i)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rays = 0
+    launches = 0
+    kernel_ms = 0.0
+    trace_ms = shade_ms = 0.0
+    waves = 0
+    for i in range(W, W + K):
+        st = step(i, profile=not args.no_profile)
+        rays += st.rays
+        launches += st.kernel_launches
+        kernel_ms += st.device_ms
+        trace_ms += st.trace_ms
+        shade_ms += st.shade_ms
+        waves += st.profiled_waves
+    e1.record()
+    barrier()
+    ck = clocks.stop()
+    span_ms = e0.elapsed_time(e1)
+    prof_rays = rays
+    if args.no_profile:  # one extra (untimed) profiled step for the per-kernel durations
+        st = step(W + K - 1, profile=True)
+        trace_ms, shade_ms, waves, prof_rays = st.trace_ms, st.shade_ms, st.profiled_waves, st.rays
+    t = torch.tensor([span_ms, float(rays), float(launches), kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        tdist.all_reduce(tmax, op=tdist.ReduceOp.MAX)
+        tsum = t.clone()
+        tdist.all_reduce(tsum, op=tdist.ReduceOp.SUM)
+        span_ms, rays_all, launches_all = float(tmax[0]), float(tsum[1]), int(tsum[2])
+    else:
+        rays_all, launches_all = float(rays), launches
+    value = rays_all / span_ms / 1e3
+    samples_all = float(NX) * NY * S * K * world
+
+    # ---- e2e: C ABI with host buffers, every step builds, renders, reads back ----
+    e2e = None
+    if not args.no_e2e:
+        host_fb = np.empty((NY, NX, 3), dtype=np.float32)
+        h2d = d2h = 0
+        e2e_rays = 0
+        Ke = K
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            s2 = pyrt.Scene(SCENE_ID, NX, NY, texture_dir=tex, device=local)
+            st = s2.render(spp=spp_all, rng_mode=0, split_mode=1, rank=(W + i) * world + rank, world=passes)
+            if world > 1:
+                rdist.reduce_sum_to_root(rdist.accum_tensor(s2))
+                torch.cuda.synchronize()
+            if rank == 0:
+                s2.resolve(total_spp=S * world)
+                pyrt._check(pyrt.lib().rt_readback(s2._h, host_fb.ctypes.data, None, None))
+                d2h += host_fb.nbytes
+            h2d += int(s2.info.h2d_bytes)
+            e2e_rays += st.rays
+            s2.close()
+        barrier()
+        dt = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([dt, float(e2e_rays)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t.clone()
+            tdist.all_reduce(tm, op=tdist.ReduceOp.MAX)
+            ts = t.clone()
+            tdist.all_reduce(ts, op=tdist.ReduceOp.SUM)
+            dt, e2e_rays = float(tm[0]), float(ts[1])
+        e2e = {"value": round(e2e_rays / dt / 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": h2d // Ke,
+               "d2h_bytes_per_step": d2h // Ke if rank == 0 else 0, "ms_per_step": round(dt / Ke, 3),
+               "what": "per step: rt_build_scene (host generator + H2D scene/texture + device BVH build) + rt_render + "
+                       "rt_readback(float fb -> host) + rt_destroy; wall clock, max over ranks"}
+
+    if rank == 0:
+        hbm, peak_src, sm_max = peaks()
+        # dominant kernel = k_trace: algorithmic bytes per launch / mean launch duration (CUDA events on the render stream)
+        n_launch = max(waves, 1)
+        rays_per_launch = prof_rays / n_launch
+        trace_s_per_launch = trace_ms / n_launch / 1e3
+        achieved = C4_TRACE_BYTES_PER_RAY * rays_per_launch / trace_s_per_launch / 1e9 if trace_ms > 0 else None
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(span_ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Book-2 final scene (create_world_final + earthmap) 800x800, depth 50, %d spp per step "
+                                   "per GPU; default 10 steps = the 10000-spp config" % S,
+                       "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": S, "spp_total": S * K * world,
+                       "max_depth": 50, "rng": "philox4x32-10", "parallelism": "spp-split x%d, scene replicated" % world,
+                       "l2": "inputs larger than L2: %.0f MB of path state (%d slots x 88 B) streamed every wave" %
+                             (st.n_slots * 88 / 1e6, st.n_slots)},
+            "msamples_per_s": round(samples_all / span_ms / 1e3, 3),
+            "rays": int(rays_all), "rays_per_sample": round(rays_all / samples_all, 4),
+            "kernel_ms_per_step": round(kernel_ms / K, 3),
+            "gpu_launches": launches_all,
+            "clocks": ck,
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 1) if achieved else None,
+                         "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4) if achieved else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_ray": C4_TRACE_BYTES_PER_RAY,
+                         "rays_per_launch": round(rays_per_launch, 1), "launch_ms": round(trace_ms / n_launch, 5),
+                         "share_of_kernel_time": {"k_trace": round(trace_ms / max(trace_ms + shade_ms, 1e-9), 4),
+                                                  "k_shade": round(shade_ms / max(trace_ms + shade_ms, 1e-9), 4)},
+                         "note": "the working set of C4 is L2-resident (SURVEY.md §8d): HBM-equivalent bytes of the "
+                                 "reference algorithm; see roofline_fp32 for the ALU roof"},
+            "roofline_fp32": {"achieved_tflops": round(value * 1e6 / world * C4_FLOP_PER_RAY / 1e12, 3),
+                              "peak_tflops": round(fp32_peak, 1),
+                              "frac": round(value * 1e6 / world * C4_FLOP_PER_RAY / 1e12 / fp32_peak, 4),
+                              "flop_per_ray": C4_FLOP_PER_RAY, "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz"},
+        }
+        if world == 1 and not args.no_reference_cuda:
+            sc.close()
+            line["reference_cuda_sm100"] = reference_cuda_run()
+            rc = line["reference_cuda_sm100"]
+            if rc and "value" in rc and rc["value"]:
+                line["speedup_vs_reference_cuda_sm100"] = round(value / rc["value"], 1)
+        if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_CPU):
+            try:
+                threads = os.cpu_count() or 1
+                ns, _ = cpu_sample_plan(threads, 12.0)
+                o = cpu_reference_run(NX, NY, ns, threads, count=1)
+                line["cpu_baseline"] = {"value": round(o["mrays_per_s"], 4), "unit": UNIT, "cores": threads,
+                                        "kind": "reference",
+                                        "sample": "%dx%d x %d spp of the same scene (reference render() compiled for the "
+                                                  "host behind oracle/shim)" % (NX, NY, ns)}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "failed: %r" % (e,)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.barrier(device_ids=[local])
+        tdist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,6 +48,8 @@ typedef struct rt_render_params {
   int32_t rank, world;     /* this process's share; world <= 0 means 1 */
   int32_t substreams;      /* path slots per pixel; <= 0: automatic. Forced to 1 in reference-RNG mode */
   int32_t aov;             /* != 0: also produce primary-hit object id / material id / t buffers */
+  int32_t accumulate;      /* != 0: progressive pass: the linear sums of this call are ADDED to the accumulation buffer of the
+                              previous call (same resolution and split); resolve with rt_resolve(total spp so far) */
   int32_t profile;         /* != 0: CUDA events around every k_trace / k_shade launch (rt_render_stats.trace_ms / shade_ms) */
 } rt_render_params;
 
