@@ -75,7 +75,7 @@ struct rt_scene {
   DBuf<int> list0, list1, queues;
   DBuf<WaveCounters> counters;
   WaveCounters* h_counters = nullptr;  // pinned
-  DBuf<float> accum, fb, aov_t; DBuf<int> aov_obj, aov_mat;
+  DBuf<float> accum, fb, aov_t; DBuf<int> aov_obj, aov_mat; DBuf<unsigned long long> acc64;
   size_t slots_cap = 0, pix_cap = 0, accum_valid_pix = 0;
   RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
   ~rt_scene() {
@@ -348,7 +348,7 @@ static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rn
   }
   if (ref_rng && s->rng.n < 6 * n_slots) CU(s->rng.alloc(6 * s->slots_cap));
   if (n_pix > s->pix_cap) {
-    CU(s->accum.alloc(3 * n_pix)); CU(s->fb.alloc(3 * n_pix));
+    CU(s->accum.alloc(3 * n_pix)); CU(s->fb.alloc(3 * n_pix)); CU(s->acc64.alloc(3 * n_pix));
     s->aov_obj.free(); s->aov_mat.free(); s->aov_t.free();
     s->pix_cap = n_pix; s->accum_valid_pix = 0;
   }
@@ -378,32 +378,37 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     P.sample_base = 0; P.sample_count = spp_total;
   }
   const size_t n_pix = (size_t)P.rows_local * P.nx;
-  int S = p->substreams;
-  if (S <= 0) {
-    long long target = 2 * 1024 * 1024;
-    if (const char* e = getenv("RT_SLOTS")) target = atoll(e);
-    S = (int)std::max<long long>(1, (target + (long long)n_pix / 2) / std::max<size_t>(n_pix, 1));
+  P.work_total = (long long)n_pix * P.sample_count;
+  if (ref_rng) {
+    P.n_slots = (int)n_pix;  // a slot is a pixel: one sequential XORWOW stream each
+  } else {
+    long long target = p->slots > 0 ? p->slots : 1024 * 1024;
+    if (p->slots <= 0) if (const char* e = getenv("RT_SLOTS")) target = atoll(e);
+    target = (target + 127) / 128 * 128;
+    P.n_slots = (int)std::max<long long>(0, std::min<long long>(target, P.work_total));
   }
-  if (ref_rng) S = 1;
-  S = std::max(1, std::min(S, std::max(P.sample_count, 1)));
-  P.substreams = S;
-  P.n_slots = (int)(n_pix * S);
   P.max_depth = p->max_depth > 0 ? p->max_depth : 50;
   P.tmin = p->t_min > 0 ? p->t_min : 0.001f;
   if (p->override_background) { P.background = v3(p->background[0], p->background[1], p->background[2]); P.gradient = p->gradient_bg; }
   else { P.background = v3(sd.background[0], sd.background[1], sd.background[2]); P.gradient = sd.gradient_bg; }
   P.seed = p->seed ? p->seed : 1984ull;
   const float gamma = p->gamma > 0 ? p->gamma : 2.2f;
-  if (ensure_buffers(s, P.n_slots, n_pix, ref_rng, p->aov != 0)) return 1;
+  if (ensure_buffers(s, std::max(P.n_slots, 1), n_pix, ref_rng, p->aov != 0)) return 1;
 
   PathArrays A;
   A.ray_o = s->ray_o.p; A.ray_d = s->ray_d.p; A.hit = s->hit.p; A.thr = s->thr.p; A.rad = s->rad.p; A.col = s->col.p;
-  A.rng = s->rng.p;
+  A.rng = s->rng.p; A.acc64 = s->acc64.p;
   cudaStream_t st = s->stream;
   cudaEvent_t e0, e1, ev;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CU(cudaMemsetAsync(s->counters.p, 0, sizeof(WaveCounters), st));
   CU(cudaEventRecord(e0, st));
+  {
+    WaveCounters init; memset(&init, 0, sizeof(init));
+    init.next_work = (unsigned long long)P.n_slots;  // k_start hands out the first n_slots work items itself
+    *s->h_counters = init;
+    CU(cudaMemcpyAsync(s->counters.p, s->h_counters, sizeof(WaveCounters), cudaMemcpyHostToDevice, st));
+    if (!ref_rng && n_pix > 0) CU(cudaMemsetAsync(s->acc64.p, 0, 3 * n_pix * sizeof(unsigned long long), st));
+  }
   const int B = 128;
   int launches = 0, waves = 0, prof_waves = 0;
   double prof_trace_ms = 0.0, prof_shade_ms = 0.0;
@@ -454,7 +459,9 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   {
     const int Gp = (int)((n_pix + 255) / 256);
     if (n_pix > 0) {
-      k_accumulate<<<Gp, 256, 0, st>>>(P, A, s->accum.p, (p->accumulate != 0 && s->accum_valid_pix == n_pix) ? 1 : 0);
+      const int add = (p->accumulate != 0 && s->accum_valid_pix == n_pix) ? 1 : 0;
+      if (ref_rng) k_accumulate<RNG_REFERENCE><<<Gp, 256, 0, st>>>(P, A, s->accum.p, add);
+      else k_accumulate<RNG_PHILOX><<<Gp, 256, 0, st>>>(P, A, s->accum.p, add);
       s->accum_valid_pix = n_pix;
       k_resolve<<<Gp, 256, 0, st>>>((int)n_pix, spp_total, gamma, s->accum.p, s->fb.p);
       launches += 2;
@@ -475,7 +482,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   memset(&R, 0, sizeof(R));
   R.device_ms = ms; R.rays = s->h_counters->rays; R.samples = (uint64_t)n_pix * (uint64_t)P.sample_count;
   R.waves = waves; R.kernel_launches = launches; R.rows_local = P.rows_local; R.nx = P.nx;
-  R.substreams = S; R.n_slots = P.n_slots; R.stack_overflow = s->h_counters->overflow;
+  R.nonfinite_samples = s->h_counters->nonfinite; R.n_slots = P.n_slots; R.stack_overflow = s->h_counters->overflow;
   R.profiled_waves = prof_waves; R.trace_ms = prof_trace_ms; R.shade_ms = prof_shade_ms;
   if (device_ms) *device_ms = ms;
   if (rays) *rays = R.rays;

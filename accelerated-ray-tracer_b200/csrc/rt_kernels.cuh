@@ -14,9 +14,14 @@
 //   k_resolve  per pixel: sum the slot partials, scale by 1/ns, gamma        (main.cu:128-132)
 //   k_aov      primary-hit object/material id + t for the centre ray of every pixel
 //
-// A slot is bound to one pixel and one sub-stream q of that pixel's samples (samples q, q+S, ...),
-// so per-pixel sums need no atomics and are deterministic. In reference-RNG mode S = 1 and a slot
-// consumes its pixel's XORWOW stream in exactly the reference's order.
+// Philox mode (production): a slot is a worker. Work item w = sample * n_local_pixels + local_pixel is
+// handed out by one 64-bit counter (warp-aggregated), so every slot stays busy until the whole job is
+// done no matter how unevenly path lengths are spread over the image (on the Book-2 final scene the
+// pixel-bound scheme ran at 11% mean slot occupancy). A finished sample is added to its pixel with
+// 64-bit FIXED-POINT atomics (2^-32 resolution): integer sums do not depend on the order of arrival,
+// so the image is bit-reproducible and identical under any tile split.
+// Reference-RNG mode (validation): a slot IS a pixel and consumes that pixel's XORWOW stream in exactly
+// the reference's order, samples one after the other, summed in float like `col += color(...)`.
 #pragma once
 #include "rt_shade.cuh"
 
@@ -28,8 +33,9 @@ struct PathArrays {
   float2* hit;     // t, top-level object index (int bits; -1 = miss)
   float4* thr;     // throughput.rgb, bounce (int bits)
   float4* rad;     // radiance.rgb of the current sample, sample number (int bits)
-  float4* col;     // sum of finished samples.rgb, -
+  float4* col;     // reference-RNG mode: float sum of the pixel's finished samples
   uint32_t* rng;   // reference-RNG mode: 6 words per slot, SoA [6][n_slots]
+  unsigned long long* acc64;  // Philox mode: per local pixel 3 x fixed-point (2^-32) radiance sums
 };
 
 struct WaveCounters {
@@ -38,15 +44,16 @@ struct WaveCounters {
   unsigned long long rays;     // closest-hit queries issued (= the reference's bounce-loop iterations)
   unsigned long long samples;  // finished samples
   unsigned int overflow;       // traversal stack overflow flag (must stay 0)
-  int pad;
+  unsigned int nonfinite;      // Philox mode: samples dropped because their radiance was inf/NaN
+  unsigned long long next_work; // Philox mode: next work item to hand out
 };
 
 struct RenderParams {
   int nx, ny;            // full image
   int rows_local;        // scanlines owned by this rank (tile split: j = lr * world + rank)
   int rank, world;
-  int n_slots;           // rows_local * nx * substreams
-  int substreams;        // S
+  int n_slots;           // path slots in flight (reference-RNG mode: one per local pixel)
+  long long work_total;  // rows_local * nx * sample_count work items (Philox mode)
   int sample_base;       // first sample number of this rank's share (spp split), else 0
   int sample_count;      // samples per pixel this rank renders
   int max_depth;         // 50
@@ -57,12 +64,10 @@ struct RenderParams {
 
 enum RngMode : int { RNG_PHILOX = 0, RNG_REFERENCE = 1 };
 
-struct SlotInfo { int lpix, i, j, pix, sub; };
-RT_D SlotInfo slot_info(const RenderParams& P, int slot) {
+struct SlotInfo { int lpix, i, j, pix; };
+RT_D SlotInfo pixel_info(const RenderParams& P, int lpix) {
   SlotInfo s;
-  const int npl = P.rows_local * P.nx;
-  s.sub = slot / npl;
-  s.lpix = slot - s.sub * npl;
+  s.lpix = lpix;
   const int lr = s.lpix / P.nx;
   s.i = s.lpix - lr * P.nx;
   s.j = lr * P.world + P.rank;
@@ -96,11 +101,12 @@ RT_D void rng_store(const Xorwow& g, const PathArrays& A, const RenderParams& P,
 // New camera sample for a slot (main.cu:121-123): jitter, lens, shutter time; throughput 1, radiance 0.
 template <class RNG>
 RT_D void start_sample(const DScene& S, const RenderParams& P, const PathArrays& A, int slot, const SlotInfo& si, int sample, RNG& g) {
+  // ray_d.w carries the slot's local pixel, rad.w its sample number
   const float u = fdiv(fadd((float)si.i, g.uniform()), (float)P.nx);
   const float v = fdiv(fadd((float)si.j, g.uniform()), (float)P.ny);
   Ray r = camera_get_ray(S.cam, u, v, g);
   A.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
-  A.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);
+  A.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(si.lpix));
   A.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
   A.rad[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(sample));
 }
@@ -117,21 +123,51 @@ RT_D int warp_append(int* counter, bool pred) {
   return base + __popc(m & ((1u << lane) - 1u));
 }
 
+// Warp-aggregated grab of consecutive work items: lanes with `pred` get w, w+1, ... in lane order.
+RT_D unsigned long long warp_grab(unsigned long long* counter, bool pred) {
+  const unsigned m = __ballot_sync(__activemask(), pred);
+  if (!pred) return ~0ull;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+}
+#define RT_FIXED_ONE 4294967296.0f  /* 2^32 */
+RT_D void fixed_add(unsigned long long* acc, float v) {
+  atomicAdd(acc, (unsigned long long)__float2ll_rn(v * RT_FIXED_ONE));  // two's complement: negative values add correctly
+}
+RT_D void work_to_pixel_sample(const RenderParams& P, unsigned long long w, int& lpix, int& sample) {
+  const unsigned long long npl = (unsigned long long)(P.rows_local * P.nx);
+  const unsigned long long s = w / npl;
+  lpix = (int)(w - s * npl);
+  sample = P.sample_base + (int)s;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128) k_start(DScene S, RenderParams P, PathArrays A, int* list0, WaveCounters* C) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= P.n_slots) return;
-  const SlotInfo si = slot_info(P, slot);
-  A.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
   typename RngOf<MODE>::type g;
-  if constexpr (MODE == RNG_REFERENCE) { g.init((unsigned long long)(long long)(1984 + si.pix)); }  // render_init, main.cu:104
-  const bool live = si.sub < P.sample_count;
-  if (live) {
-    const int sample = P.sample_base + si.sub;
-    if constexpr (MODE == RNG_PHILOX) rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-    start_sample(S, P, A, slot, si, sample, g);
+  bool live;
+  if constexpr (MODE == RNG_REFERENCE) {
+    const SlotInfo si = pixel_info(P, slot);  // slot == local pixel
+    A.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    g.init((unsigned long long)(long long)(1984 + si.pix));  // render_init, main.cu:104
+    live = P.sample_count > 0;
+    if (live) start_sample(S, P, A, slot, si, P.sample_base, g);
+    rng_store(g, A, P, slot);
+  } else {
+    live = (long long)slot < P.work_total;  // the first n_slots work items; the counter starts behind them
+    if (live) {
+      int lpix, sample;
+      work_to_pixel_sample(P, (unsigned long long)slot, lpix, sample);
+      const SlotInfo si = pixel_info(P, lpix);
+      rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
+      start_sample(S, P, A, slot, si, sample, g);
+    }
   }
-  if constexpr (MODE == RNG_REFERENCE) rng_store(g, A, P, slot);
   const int pos = warp_append(&C->n_active[0], live);
   if (live) list0[pos] = slot;
 }
@@ -181,12 +217,12 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, RenderParams P, PathArr
   }
   const int pos = gid - base;
   const bool valid = pos < qcount;
-  bool alive = false;
+  bool alive = false, want_work = false;
   int slot = -1;
   if (valid) {
     slot = queues[(size_t)q * P.n_slots + pos];
-    const SlotInfo si = slot_info(P, slot);
     const float4 o = A.ray_o[slot], d = A.ray_d[slot];
+    SlotInfo si = pixel_info(P, __float_as_int(d.w));
     float4 thr4 = A.thr[slot], rad4 = A.rad[slot];
     Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
     V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(rad4.x, rad4.y, rad4.z);
@@ -233,25 +269,50 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, RenderParams P, PathArr
       }
       sample_done = !scattered || bounce >= P.max_depth;
     }
-    if (sample_done) {
-      // render: col += color(...) (main.cu:124), then the next sample of this slot, if any
-      float4 c = A.col[slot];
-      c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
-      A.col[slot] = c;
-      sample += P.substreams;
-      if (sample < P.sample_base + P.sample_count) {
-        if constexpr (MODE == RNG_PHILOX) rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-        start_sample(S, P, A, slot, si, sample, g);
-        alive = true;
+    if constexpr (MODE == RNG_REFERENCE) {
+      if (sample_done) {
+        // render: col += color(...) (main.cu:124), then the next sample of this pixel, if any
+        float4 c = A.col[slot];
+        c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
+        A.col[slot] = c;
+        ++sample;
+        if (sample < P.sample_base + P.sample_count) {
+          start_sample(S, P, A, slot, si, sample, g);
+          alive = true;
+        }
       }
     } else {
+      if (sample_done) {
+        if (isfinite(rad.x) && isfinite(rad.y) && isfinite(rad.z)) {
+          unsigned long long* acc = A.acc64 + 3 * (size_t)si.lpix;
+          fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
+        } else {
+          atomicAdd(&C->nonfinite, 1u);
+        }
+      }
+    }
+    if (!sample_done) {
       A.ray_o[slot] = make_float4(next.o.x, next.o.y, next.o.z, next.tm);
-      A.ray_d[slot] = make_float4(next.d.x, next.d.y, next.d.z, 0.f);
+      A.ray_d[slot] = make_float4(next.d.x, next.d.y, next.d.z, d.w);
       A.thr[slot] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce));
       A.rad[slot] = make_float4(rad.x, rad.y, rad.z, __int_as_float(sample));
       alive = true;
     }
     rng_store(g, A, P, slot);
+    if constexpr (MODE == RNG_PHILOX) want_work = sample_done;
+  }
+  if constexpr (MODE == RNG_PHILOX) {
+    // path regeneration: finished lanes take the next work items (consecutive pixels of one sample number)
+    const unsigned long long w = warp_grab(&C->next_work, want_work);
+    if (want_work && w < (unsigned long long)P.work_total) {
+      int lpix, sample;
+      work_to_pixel_sample(P, w, lpix, sample);
+      const SlotInfo si = pixel_info(P, lpix);
+      Philox g;
+      rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
+      start_sample(S, P, A, slot, si, sample, g);
+      alive = true;
+    }
   }
   const int np = warp_append(&C->n_active[parity ^ 1], alive);
   if (alive) next_list[np] = slot;
@@ -265,14 +326,20 @@ RT_D float apply_gamma(float c, float gamma) {  // main.cu:37-42
 
 // accum: linear sum over this rank's samples per LOCAL pixel (float3); the unit the NCCL reduce sums.
 // add != 0: progressive pass, accum += this pass (rt_render_params.accumulate).
+template <int MODE>
 __global__ void k_accumulate(RenderParams P, PathArrays A, float* accum, int add) {
   const int lpix = blockIdx.x * blockDim.x + threadIdx.x;
   const int npl = P.rows_local * P.nx;
   if (lpix >= npl) return;
-  float x = 0.f, y = 0.f, z = 0.f;
-  for (int s = 0; s < P.substreams; ++s) {
-    const float4 c = A.col[(size_t)s * npl + lpix];
-    x = (s == 0) ? c.x : fadd(x, c.x); y = (s == 0) ? c.y : fadd(y, c.y); z = (s == 0) ? c.z : fadd(z, c.z);
+  float x, y, z;
+  if constexpr (MODE == RNG_REFERENCE) {
+    const float4 c = A.col[lpix];
+    x = c.x; y = c.y; z = c.z;
+  } else {
+    const double k = 1.0 / 4294967296.0;
+    x = (float)((double)(long long)A.acc64[3 * (size_t)lpix + 0] * k);
+    y = (float)((double)(long long)A.acc64[3 * (size_t)lpix + 1] * k);
+    z = (float)((double)(long long)A.acc64[3 * (size_t)lpix + 2] * k);
   }
   if (add) { x = fadd(accum[3 * lpix + 0], x); y = fadd(accum[3 * lpix + 1], y); z = fadd(accum[3 * lpix + 2], z); }
   accum[3 * lpix + 0] = x; accum[3 * lpix + 1] = y; accum[3 * lpix + 2] = z;

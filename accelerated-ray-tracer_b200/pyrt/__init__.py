@@ -33,7 +33,7 @@ class RenderParamsC(C.Structure):
     _fields_ = [("spp", C.c_int32), ("max_depth", C.c_int32), ("gamma", C.c_float), ("t_min", C.c_float),
                 ("background", C.c_float * 3), ("gradient_bg", C.c_int32), ("override_background", C.c_int32),
                 ("seed", C.c_uint64), ("rng_mode", C.c_int32), ("split_mode", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("substreams", C.c_int32), ("aov", C.c_int32), ("accumulate", C.c_int32),
+                ("world", C.c_int32), ("slots", C.c_int32), ("aov", C.c_int32), ("accumulate", C.c_int32),
                 ("profile", C.c_int32)]
 
 
@@ -48,7 +48,7 @@ class SceneInfoC(C.Structure):
 class RenderStatsC(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("rays", C.c_uint64), ("samples", C.c_uint64), ("waves", C.c_int32),
                 ("kernel_launches", C.c_int32), ("rows_local", C.c_int32), ("nx", C.c_int32),
-                ("substreams", C.c_int32), ("n_slots", C.c_int32), ("stack_overflow", C.c_uint32),
+                ("nonfinite_samples", C.c_int32), ("n_slots", C.c_int32), ("stack_overflow", C.c_uint32),
                 ("profiled_waves", C.c_int32), ("trace_ms", C.c_double), ("shade_ms", C.c_double)]
 
 
@@ -268,7 +268,7 @@ class Scene:
     def __exit__(self, *a):
         self.close()
 
-    def render(self, spp=0, rng_mode=0, rank=0, world=1, split_mode=0, substreams=0, aov=False, seed=0,
+    def render(self, spp=0, rng_mode=0, rank=0, world=1, split_mode=0, slots=0, aov=False, seed=0,
                max_depth=0, gamma=0.0, background=None, gradient_bg=None, profile=False, accumulate=False):
         p = RenderParamsC()
         p.spp, p.max_depth, p.gamma, p.t_min = spp, max_depth, gamma, 0.0
@@ -277,7 +277,7 @@ class Scene:
             p.background[0], p.background[1], p.background[2] = background
             p.gradient_bg = int(bool(gradient_bg))
         p.seed, p.rng_mode, p.split_mode, p.rank, p.world = seed, rng_mode, split_mode, rank, world
-        p.substreams, p.aov, p.profile = substreams, int(bool(aov)), int(bool(profile))
+        p.slots, p.aov, p.profile = slots, int(bool(aov)), int(bool(profile))
         p.accumulate = int(bool(accumulate))
         ms, rays = C.c_double(0), C.c_uint64(0)
         _check(lib().rt_render(self._h, C.byref(p), C.byref(ms), C.byref(rays)))

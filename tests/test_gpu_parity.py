@@ -120,15 +120,21 @@ def test_converged_image_philox_vs_reference(pyrt, golden, name, sid, nx, ny, re
         sc.render(spp=ref_spp, rng_mode=0, seed=777)
         fb_same_spp = sc.framebuffer()
     gfb = g["fb"]
-    mean_err = np.abs(np.clip(fb, 0, 1).mean(axis=(0, 1)) - np.clip(gfb, 0, 1).mean(axis=(0, 1)))
+    # mean error at EQUAL spp: gamma (and the [0,1] clip) are concave, so a noisier estimate has a lower mean after
+    # them (Jensen); comparing our 16x-spp image with the golden would measure that bias, not a difference
+    mean_err = np.abs(np.clip(fb_same_spp, 0, 1).mean(axis=(0, 1)) - np.clip(gfb, 0, 1).mean(axis=(0, 1)))
     assert float(mean_err.max()) <= 1.0 / 255.0, "per-channel mean error %s" % mean_err
+    # and in LINEAR radiance (gamma undone), where the estimator is unbiased at any spp: within 1 %
+    lin, glin = np.maximum(fb, 0).astype(np.float64) ** 2.2, np.maximum(gfb, 0).astype(np.float64) ** 2.2
+    rel = np.abs(lin.mean(axis=(0, 1)) - glin.mean(axis=(0, 1))) / glin.mean(axis=(0, 1))
+    assert float(rel.max()) <= 0.01, "linear-radiance mean differs by %s" % rel
 
     def box(x):
         return np.clip(x, 0, 1).reshape(ny // 4, 4, nx // 4, 4, 3).mean(axis=(1, 3))
     p_box = _psnr(box(fb), box(gfb))
     p_raw = _psnr(fb, gfb)
     p_floor = _psnr(fb, fb_same_spp)  # our own noise at the golden's spp: what the golden's noise alone costs
-    print("%s: mean_err=%s psnr_raw=%.2f psnr_box4=%.2f psnr_self_noise=%.2f" % (name, mean_err, p_raw, p_box, p_floor))
+    print("%s: mean_err=%s lin_rel=%s psnr_raw=%.2f psnr_box4=%.2f psnr_self_noise=%.2f" % (name, mean_err, rel, p_raw, p_box, p_floor))
     assert p_box >= 40.0, "PSNR (4x4 box) %.2f dB" % p_box
     assert p_raw >= p_floor - 1.0, "raw PSNR %.2f dB is below the Monte-Carlo noise floor %.2f dB" % (p_raw, p_floor)
 
@@ -222,11 +228,11 @@ def test_philox_is_deterministic_and_seed_dependent(pyrt):
         b = sc.framebuffer()
         sc.render(spp=8, rng_mode=0, seed=5)
         c = sc.framebuffer()
-        sc.render(spp=8, rng_mode=0, substreams=1)
+        sc.render(spp=8, rng_mode=0, slots=4096)
         d = sc.framebuffer()
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert not np.array_equal(a, c)
-    assert float(np.abs(a - d).max()) < 1e-4  # slot layout only changes the summation order
+    assert np.array_equal(a.view(np.uint32), d.view(np.uint32))  # fixed-point sums: independent of the slot count
 
 
 def test_scale_up_c5_bvh_matches_brute_force_ids(pyrt, built):

@@ -73,7 +73,7 @@ def speed(sid, nx, ny, spp, reps=2):
     best = min(x[0] for x in res[1:])
     o = {"speed": pyrt.SCENE_NAMES[sid], "nx": nx, "ny": ny, "spp": spp, "ms_best": round(best, 3), "rays": int(rays),
          "mrays_per_s": round(rays / best / 1e3, 1), "waves": st.waves, "launches": st.kernel_launches, "slots": st.n_slots,
-         "substreams": st.substreams, "bvh_nodes": sc.info.n_bvh_nodes}
+         "bvh_nodes": sc.info.n_bvh_nodes}
     sc.close()
     return o
 

@@ -13,7 +13,6 @@ if [[ $WHAT == all || $WHAT == *tests* ]]; then
 fi
 if [[ $WHAT == all || $WHAT == *bench* ]]; then
   timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cat $O/bench.json; tail -3 $O/bench.err
-  timeout 600 python bench.py --no-profile --no-e2e --no-cpu-baseline --no-reference-cuda --steps 3 > $O/bench_noprofile.json 2>> $O/bench.err; cat $O/bench_noprofile.json
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2>> $O/bench.err; cat $O/bench_reference.json
 fi
 if [[ $WHAT == all || $WHAT == *wavelog* ]]; then
@@ -28,3 +27,6 @@ if [[ $WHAT == all || $WHAT == *ncu* ]]; then
   echo "ncu full rc=$?"; tail -3 $O/ncu_full.log
 fi
 ls -la $O | head -40
+if [[ $WHAT == *slots* ]]; then
+  for n in 262144 524288 1048576 2097152 4194304; do RT_SLOTS=$n timeout 300 python tools/prof_cmd.py 300; done > $O/slots_sweep.txt 2>&1; cat $O/slots_sweep.txt
+fi
