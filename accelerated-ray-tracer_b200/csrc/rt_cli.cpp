@@ -1,0 +1,85 @@
+// rt_cli.cpp — command-line front end of librt_b200.so: replaces the reference's main() and its ten
+// hard-wired scene functions (main.cu:654-1322). Like the reference it writes an ASCII P3 PPM to
+// stdout and diagnostics to stderr, and exits 99 on a CUDA/library error (main.cu:23-35). Unlike the
+// reference the scene, resolution, spp and GPU count are arguments (the reference picks the scene with
+// a hard-coded `switch (10)`, main.cu:1309).
+//
+//   rt_cli --scene 9 [--nx 800 --ny 800] [--spp 10000] [--rng philox|reference] [--gpus N]
+//          [--textures DIR] [--out file.ppm] [--depth 50] [--seed 1984] [--grid-half G]
+//
+// --gpus N: tile split over N devices of this box from ONE process (one host thread per GPU, scene
+// replicated, interleaved scanlines; the shares are assembled on the host). Bit-identical to N = 1.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include "rt_api.h"
+
+struct Share { int rc = 0; std::string err; std::vector<float> fb; rt_render_stats st{}; rt_scene_info info{}; };
+
+int main(int argc, char** argv) {
+  rt_scene_desc d; memset(&d, 0, sizeof(d));
+  rt_render_params p; memset(&p, 0, sizeof(p));
+  d.scene_id = 10;  // what the reference's main() runs
+  d.device = -1;
+  int gpus = 1;
+  std::string tex = "textures", out;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto val = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
+    if (a == "--scene") d.scene_id = atoi(val());
+    else if (a == "--nx") d.nx = atoi(val());
+    else if (a == "--ny") d.ny = atoi(val());
+    else if (a == "--grid-half") d.grid_half = atoi(val());
+    else if (a == "--spp") p.spp = atoi(val());
+    else if (a == "--depth") p.max_depth = atoi(val());
+    else if (a == "--seed") p.seed = strtoull(val(), nullptr, 10);
+    else if (a == "--rng") { std::string v = val(); p.rng_mode = (v == "reference" || v == "ref" || v == "xorwow") ? 1 : 0; }
+    else if (a == "--gpus") gpus = atoi(val());
+    else if (a == "--textures") tex = val();
+    else if (a == "--out") out = val();
+    else if (a == "--help" || a == "-h") {
+      fprintf(stderr, "usage: rt_cli --scene 1..10 [--nx N --ny N] [--spp N] [--rng philox|reference] [--gpus N] [--textures DIR] [--out f.ppm]\n");
+      return 0;
+    } else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+  }
+  if (gpus < 1) gpus = 1;
+  d.texture_dir = tex.c_str();
+  std::vector<Share> sh(gpus);
+  std::vector<std::thread> th;
+  for (int r = 0; r < gpus; ++r)
+    th.emplace_back([&, r]() {
+      Share& S = sh[r];
+      rt_scene_desc dd = d; dd.device = gpus > 1 ? r : d.device;
+      rt_render_params pp = p; pp.rank = r; pp.world = gpus; pp.split_mode = 0;
+      rt_scene* sc = nullptr;
+      if ((S.rc = rt_build_scene(&dd, &sc)) != 0) { S.err = rt_last_error(); return; }
+      rt_scene_info_get(sc, &S.info);
+      if ((S.rc = rt_render(sc, &pp, nullptr, nullptr)) != 0) { S.err = rt_last_error(); rt_destroy(sc); return; }
+      rt_render_stats_get(sc, &S.st);
+      S.fb.resize((size_t)S.st.rows_local * S.st.nx * 3);
+      if ((S.rc = rt_readback(sc, S.fb.data(), nullptr, nullptr)) != 0) S.err = rt_last_error();
+      rt_destroy(sc);
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < gpus; ++r)
+    if (sh[r].rc) { fprintf(stderr, "rt_cli: GPU %d: %s\n", r, sh[r].err.c_str()); return 99; }
+  const int nx = sh[0].info.nx, ny = sh[0].info.ny;
+  std::vector<float> img((size_t)nx * ny * 3);
+  unsigned long long rays = 0; double ms = 0;
+  for (int r = 0; r < gpus; ++r) {
+    for (int lr = 0; lr < sh[r].st.rows_local; ++lr)
+      memcpy(&img[(size_t)(lr * gpus + r) * nx * 3], &sh[r].fb[(size_t)lr * nx * 3], (size_t)nx * 3 * sizeof(float));
+    rays += sh[r].st.rays; if (sh[r].st.device_ms > ms) ms = sh[r].st.device_ms;
+  }
+  fprintf(stderr, "Rendering a %dx%d image, scene %d, %d GPU(s): %.3f ms on the device, %llu rays, %.1f Mrays/s\n", nx, ny,
+          d.scene_id, gpus, ms, rays, ms > 0 ? rays / ms / 1e3 : 0.0);
+  // bouncing_spheres alone scales with a double 255.99 (main.cu:722-724)
+  if (rt_write_ppm(out.empty() ? nullptr : out.c_str(), img.data(), nx, ny, d.scene_id == 1 ? 1 : 0) < 0) {
+    fprintf(stderr, "rt_cli: %s\n", rt_last_error());
+    return 99;
+  }
+  return 0;
+}

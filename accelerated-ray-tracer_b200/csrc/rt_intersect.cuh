@@ -203,13 +203,27 @@ RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
 // to the leaf child's box, which is the object's box bit for bit); interior boxes are exact unions,
 // and the slab test is monotone in the box, so they never reject a ray a leaf box would accept.
 // Exact-t ties are resolved as the reference's in-order leaf walk would (later leaf wins iff its own
-// test is inclusive), using the precomputed leaf rank.
+// test is inclusive), using the precomputed leaf rank — so the result does not depend on the order
+// in which this traversal meets the leaves.
+//
+// Execution model: the WHOLE WARP calls closest_hit (lanes without a ray pass active = false) and
+// alternates between two warp-uniform phases, chosen by ballot:
+//   node phase   lanes that hold a node expand it: 4 slab tests, sorting network, nearest interior child
+//                becomes the next node, the others go to the lane's stack, leaf children go to the
+//                lane's pending-leaf queue;
+//   leaf phase   all lanes drain their queues together, one primitive class at a time (spheres, then
+//                quads/boxes/instances, then media), so that a warp runs ONE intersection routine at a
+//                time instead of interleaving node steps, sphere, box and medium code lane by lane.
+// (First version: leaf tests inline in the node loop ran at 2-6 active lanes per instruction on the
+// Book-2 final scene, profiles/r01.)
 #define RT_STACK 48
+#define RT_LEAFQ 8         // pending leaves per lane
+#ifndef RT_NODE_MIN
+#define RT_NODE_MIN 12     // leaf phase starts when fewer lanes than this can still expand a node
+#endif
 struct Hit { float t; int tlp; };
 
-RT_D void leaf_test(const DScene& S, const Ray& r, float tmin, uint32_t ref, uint32_t tlp, Hit& best) {
-  float t;
-  if (!tlp_hit_t(S, ref, r, tmin, best.t, t)) return;
+RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, Hit& best) {
   if (t < best.t || best.tlp < 0) { best.t = t; best.tlp = (int)tlp; return; }
   // exact tie (t == best.t; only inclusive tests get here): order semantics of bvh_node::hit
   const int rn = S.tlp[tlp].rank, rb = S.tlp[best.tlp].rank;
@@ -217,58 +231,105 @@ RT_D void leaf_test(const DScene& S, const Ray& r, float tmin, uint32_t ref, uin
   if (take) { best.t = t; best.tlp = (int)tlp; }
 }
 
-RT_D Hit closest_hit(const DScene& S, const Ray& r, float tmin, float tmax0, unsigned int* overflow) {
+#define RT_CSWAP(a, b) do { if (tn[b] < tn[a]) { float tf_ = tn[a]; tn[a] = tn[b]; tn[b] = tf_; \
+  uint32_t tu_ = cr[a]; cr[a] = cr[b]; cr[b] = tu_; tu_ = ct[a]; ct[a] = ct[b]; ct[b] = tu_; } } while (0)
+
+RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
   Hit best; best.t = tmax0; best.tlp = -1;
   const float ix = frcp(r.d.x), iy = frcp(r.d.y), iz = frcp(r.d.z);  // 1.0f / direction, aabb.cuh:48
   const bool nx = ix < 0.0f, ny = iy < 0.0f, nz = iz < 0.0f;
-  uint32_t stack[RT_STACK];  // interior nodes only; leaf children are tested when their parent is visited
-  int sp = 0;
+  uint32_t stack[RT_STACK];  // interior nodes only
+  uint32_t lq_ref[RT_LEAFQ], lq_tlp[RT_LEAFQ];
+  float lq_tn[RT_LEAFQ];
+  int sp = 0, nl = 0;
   uint32_t cur = 0;
+  bool have = active;
   while (true) {
-    const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
-    const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
-    const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
-    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
-    const uint4 tl = __ldg(reinterpret_cast<const uint4*>(np + 7));
-    const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
-    const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
-    const uint32_t c4[4] = {ch.x, ch.y, ch.z, ch.w}, t4[4] = {tl.x, tl.y, tl.z, tl.w};
-    float tn[4]; uint32_t cr[4]; uint32_t ct[4];
-    int nh = 0;
+    const bool can = have && nl <= RT_LEAFQ - 4;
+    const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
+    const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, nl > 0);
+    if ((mexp | mleaf) == 0u) break;
+    if (mleaf == 0u || __popc(mexp) >= RT_NODE_MIN) {
+      // ---------------- node phase ----------------
+      if (can) {
+        const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
+        const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
+        const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+        const uint4 tl = __ldg(reinterpret_cast<const uint4*>(np + 7));
+        const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
+        const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+        float tn[4]; uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w}, ct[4] = {tl.x, tl.y, tl.z, tl.w};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0;
-      // tmin = t0 > tmin ? t0 : tmin (== fmaxf, NaN keeps tmin); reject when tmax <= tmin.
-      float t0 = fmul(fsub(nx ? hx[c] : lx[c], r.o.x), ix), t1 = fmul(fsub(nx ? lx[c] : hx[c], r.o.x), ix);
-      float lo = fmaxf(t0, tmin), hi = fminf(t1, best.t);
-      t0 = fmul(fsub(ny ? hy[c] : ly[c], r.o.y), iy); t1 = fmul(fsub(ny ? ly[c] : hy[c], r.o.y), iy);
-      lo = fmaxf(t0, lo); hi = fminf(t1, hi);
-      t0 = fmul(fsub(nz ? hz[c] : lz[c], r.o.z), iz); t1 = fmul(fsub(nz ? lz[c] : hz[c], r.o.z), iz);
-      lo = fmaxf(t0, lo); hi = fminf(t1, hi);
-      if (hi > lo && c4[c] != RT_NODE_EMPTY) {
-        int k = nh++;  // insertion sort by entry distance, nearest first
-        while (k > 0 && tn[k - 1] > lo) { tn[k] = tn[k - 1]; cr[k] = cr[k - 1]; ct[k] = ct[k - 1]; --k; }
-        tn[k] = lo; cr[k] = c4[c]; ct[k] = t4[c];
+        for (int c = 0; c < 4; ++c) {
+          // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0;
+          // tmin = t0 > tmin ? t0 : tmin (== fmaxf, NaN keeps tmin); reject when tmax <= tmin.
+          float t0 = fmul(fsub(nx ? hx[c] : lx[c], r.o.x), ix), t1 = fmul(fsub(nx ? lx[c] : hx[c], r.o.x), ix);
+          float lo = fmaxf(t0, tmin), hi = fminf(t1, best.t);
+          t0 = fmul(fsub(ny ? hy[c] : ly[c], r.o.y), iy); t1 = fmul(fsub(ny ? ly[c] : hy[c], r.o.y), iy);
+          lo = fmaxf(t0, lo); hi = fminf(t1, hi);
+          t0 = fmul(fsub(nz ? hz[c] : lz[c], r.o.z), iz); t1 = fmul(fsub(nz ? lz[c] : hz[c], r.o.z), iz);
+          lo = fmaxf(t0, lo); hi = fminf(t1, hi);
+          tn[c] = (hi > lo && cr[c] != RT_NODE_EMPTY) ? lo : FLT_MAX;  // FLT_MAX = not entered (a real entry is < best.t <= FLT_MAX)
+          if (!(hi > lo)) cr[c] = RT_NODE_EMPTY;
+        }
+        RT_CSWAP(0, 1); RT_CSWAP(2, 3); RT_CSWAP(0, 2); RT_CSWAP(1, 3); RT_CSWAP(1, 2);  // nearest first
+        // leaves -> pending queue; interior children: nearest is next, the others are stacked far-to-near
+        uint32_t next = RT_NODE_EMPTY;
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+          const uint32_t c = cr[k];
+          if (c != RT_NODE_EMPTY && (c & RT_NODE_FLAG)) {
+            if (next != RT_NODE_EMPTY) { if (sp < RT_STACK) stack[sp++] = next; else atomicOr(overflow, 1u); }
+            next = c & 0x7FFFFFFFu;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t c = cr[k];
+          if (c != RT_NODE_EMPTY && !(c & RT_NODE_FLAG)) { lq_ref[nl] = c; lq_tlp[nl] = ct[k]; lq_tn[nl] = tn[k]; ++nl; }
+        }
+        if (next != RT_NODE_EMPTY) cur = next;
+        else if (sp > 0) cur = stack[--sp];
+        else have = false;
       }
-    }
-    // leaves first-come in near-to-far order; interior children go to the stack far-to-near
-    uint32_t next = RT_NODE_EMPTY;
-    int first_interior = -1;
-    for (int k = 0; k < nh; ++k) {
-      if (cr[k] & RT_NODE_FLAG) { if (first_interior < 0) first_interior = k; continue; }
-      if (tn[k] < best.t) leaf_test(S, r, tmin, cr[k], ct[k], best);  // box test again with the updated tmax
-    }
-    if (first_interior >= 0) {
-      for (int k = nh - 1; k > first_interior; --k) {
-        if (!(cr[k] & RT_NODE_FLAG)) continue;
-        if (sp < RT_STACK) stack[sp++] = cr[k] & 0x7FFFFFFFu; else atomicOr(overflow, 1u);
+    } else {
+      // ---------------- leaf phase ----------------
+      const int nmax = __reduce_max_sync(0xFFFFFFFFu, nl);
+      // spheres
+      for (int k = 0; k < nmax; ++k) {
+        if (k < nl && ref_type(lq_ref[k]) == G_SPHERE && lq_tn[k] < best.t) {
+          float t; V3 cc;
+          if (sphere_t(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, best);
+        }
       }
-      next = cr[first_interior] & 0x7FFFFFFFu;
+      // quads, boxes, instances
+      const unsigned mgeo = __ballot_sync(0xFFFFFFFFu, [&] { bool any = false; for (int k = 0; k < nl; ++k) { const uint32_t ty = ref_type(lq_ref[k]); any |= (ty != G_SPHERE && ty != G_MEDIUM); } return any; }());
+      if (mgeo) {
+        for (int k = 0; k < nmax; ++k) {
+          if (k < nl) {
+            const uint32_t ty = ref_type(lq_ref[k]);
+            if (ty != G_SPHERE && ty != G_MEDIUM && lq_tn[k] < best.t) {
+              Rec rec;
+              if (geom_hit<false>(S, lq_ref[k], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[k], lq_tlp[k], rec.t, best);
+            }
+          }
+        }
+      }
+      // media
+      const unsigned mmed = __ballot_sync(0xFFFFFFFFu, [&] { bool any = false; for (int k = 0; k < nl; ++k) any |= ref_type(lq_ref[k]) == G_MEDIUM; return any; }());
+      if (mmed) {
+        for (int k = 0; k < nmax; ++k) {
+          if (k < nl && ref_type(lq_ref[k]) == G_MEDIUM && lq_tn[k] < best.t) {
+            float t;
+            if (medium_hit(S, S.media[ref_index(lq_ref[k])], r, tmin, best.t, t)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, best);
+          }
+        }
+      }
+      nl = 0;
     }
-    if (next != RT_NODE_EMPTY) { cur = next; continue; }
-    if (sp == 0) return best;
-    cur = stack[--sp];
   }
+  return best;
 }
 
 }  // namespace rt

@@ -180,18 +180,29 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, RenderParams P, PathArr
     C->n_active[parity ^ 1] = 0;  // the shade kernel of this wave appends here
     C->rays += (unsigned long long)n;
   }
-  if (gid >= n) return;
-  const int slot = list[gid];
-  const float4 o = A.ray_o[slot], d = A.ray_d[slot];
-  Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
-  const Hit h = closest_hit(S, r, P.tmin, FLT_MAX, &C->overflow);
-  A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp));
-  const int q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
+  if ((gid & ~31) >= n) return;  // whole warps only: closest_hit is a warp-wide routine
+  const bool active = gid < n;
+  const int slot = active ? list[gid] : 0;
+  Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
+  if (active) {
+    const float4 o = A.ray_o[slot], d = A.ray_d[slot];
+    r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+  }
+  const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
+  int q = -1;
+  if (active) {
+    A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp));
+    q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
+  }
   // bin by material class: one warp-aggregated atomic per class present in the warp
-#pragma unroll
-  for (int k = 0; k < Q_COUNT; ++k) {
-    const int pos = warp_append(&C->n_queue[parity][k], q == k);
-    if (q == k) queues[(size_t)k * P.n_slots + pos] = slot;
+  const unsigned peers = __match_any_sync(__activemask(), q);
+  if (active) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&C->n_queue[parity][q], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    queues[(size_t)q * P.n_slots + base + __popc(peers & ((1u << lane) - 1u))] = slot;
   }
 }
 
@@ -358,14 +369,19 @@ __global__ void k_resolve(int n_pix, int ns, float gamma, const float* accum, fl
 // Primary-hit AOV: centre ray of the pixel (no jitter, no lens offset, time0).
 __global__ void k_aov(DScene S, RenderParams P, int* obj, int* mat, float* tout, WaveCounters* C) {
   const int lpix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lpix >= P.rows_local * P.nx) return;
-  const int lr = lpix / P.nx, i = lpix - lr * P.nx, j = lr * P.world + P.rank;
-  const float s = fdiv(fadd((float)i, 0.5f), (float)P.nx), t = fdiv(fadd((float)j, 0.5f), (float)P.ny);
-  Ray r;
-  r.o = S.cam.origin;
-  r.d = vsub(vmad(t, S.cam.vertical, vmad(s, S.cam.horizontal, S.cam.llc)), S.cam.origin);
-  r.tm = (float)S.cam.time0;
-  const Hit h = closest_hit(S, r, P.tmin, FLT_MAX, &C->overflow);
+  const int npl = P.rows_local * P.nx;
+  if ((lpix & ~31) >= npl) return;
+  const bool active = lpix < npl;
+  Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
+  if (active) {
+    const int lr = lpix / P.nx, i = lpix - lr * P.nx, j = lr * P.world + P.rank;
+    const float s = fdiv(fadd((float)i, 0.5f), (float)P.nx), t = fdiv(fadd((float)j, 0.5f), (float)P.ny);
+    r.o = S.cam.origin;
+    r.d = vsub(vmad(t, S.cam.vertical, vmad(s, S.cam.horizontal, S.cam.llc)), S.cam.origin);
+    r.tm = (float)S.cam.time0;
+  }
+  const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
+  if (!active) return;
   obj[lpix] = h.tlp;
   mat[lpix] = h.tlp >= 0 ? S.tlp[h.tlp].mat : -1;
   tout[lpix] = h.tlp >= 0 ? h.t : 0.f;

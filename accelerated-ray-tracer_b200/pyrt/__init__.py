@@ -95,8 +95,7 @@ def _check(rc):
 
 def default_texture_dir():
     for d in (os.environ.get("RT_TEXTURE_DIR"), os.path.join(REPO_ROOT, "textures"),
-              os.path.join(REPO_ROOT, "tests", "golden", "textures"),
-              os.path.join(REPO_ROOT, "oracle", "_ref", "textures")):
+              os.path.join(REPO_ROOT, "tests", "golden", "textures")):
         if d and os.path.isdir(d):
             return d
     return "textures"

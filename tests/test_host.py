@@ -1,0 +1,196 @@
+"""CPU tests (no GPU): the C ABI loads and exports what include/rt_api.h declares, the host scene generators
+reproduce the scenes the reference built on the GPU (tests/golden), the PPM writer is byte-exact, and the
+multi-rank host logic works under torch.distributed (gloo, world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, PKG, texture_dir
+
+SCENES = [("c1_400x225_10", 1), ("c2_300x300_16", 7), ("c3_300x300_16", 8), ("c4_400x400_16", 9), ("s2_300x150_8", 2),
+          ("s3_300x150_8", 3), ("s4_300x150_8", 4), ("s5_300x150_8", 5), ("s6_300x150_8", 6), ("s10_300x150_8", 10)]
+NEEDS_TEX = {3: ["earthmap"], 9: ["earthmap"], 6: ["poolball"], 10: ["porcelain", "8ball"]}
+
+
+def test_library_exports_every_declared_symbol(pyrt):
+    hdr = open(os.path.join(ROOT, "include", "rt_api.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", hdr))
+    assert {"rt_build_scene", "rt_render", "rt_readback", "rt_destroy", "rt_last_error"} <= declared
+    lib = pyrt.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "librt_b200.so does not export %s" % name
+    assert declared == set(pyrt.EXPORTS), "pyrt.EXPORTS out of sync with include/rt_api.h"
+
+
+def test_struct_layouts_match_header(pyrt):
+    # sizes the C compiler gives the ABI structs (checked against a tiny C program built with gcc)
+    src = r'''
+#include <stdio.h>
+#include "rt_api.h"
+#include "rt_scene_desc.h"
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rt_scene_desc), sizeof(rt_render_params),
+  sizeof(rt_scene_info), sizeof(rt_render_stats), sizeof(rt_texture_desc), sizeof(rt_material_desc), sizeof(rt_object_desc),
+  sizeof(rt_camera_desc), sizeof(rt_sd_header)); return 0; }
+'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    sizes = [int(x) for x in out]
+    assert sizes[:4] == [C.sizeof(pyrt.SceneDescC), C.sizeof(pyrt.RenderParamsC), C.sizeof(pyrt.SceneInfoC), C.sizeof(pyrt.RenderStatsC)]
+    assert sizes[4:] == [pyrt.TEX_DT.itemsize, pyrt.MAT_DT.itemsize, pyrt.OBJ_DT.itemsize, pyrt.CAM_DT.itemsize, pyrt.HDR_DT.itemsize]
+
+
+def test_no_cpu_fallback(pyrt):
+    """Without a CUDA device the render path must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pyrt.RtError, match="no CUDA device"):
+        pyrt.Scene(7, 16, 16)
+    # and the product never loads, links or calls the oracle
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                for needle in ("oracle_py", "liboracle", "rt_oracle", "oracle/", "ref_cpu"):
+                    assert needle not in txt, "%s mentions %s" % (f, needle)
+
+
+def _fkey_close(a, b, tol):
+    """Deep compare of SD keys: ints/strings exact, float bit patterns within `tol` ulps."""
+    if isinstance(a, tuple) and isinstance(b, tuple):
+        return len(a) == len(b) and all(_fkey_close(x, y, tol) for x, y in zip(a, b))
+    if isinstance(a, int) and isinstance(b, int) and (a > 1 << 16 or b > 1 << 16):
+        return abs(a - b) <= tol
+    return a == b
+
+
+@pytest.mark.parametrize("name,sid", SCENES, ids=[s[0] for s in SCENES])
+def test_host_generators_reproduce_reference_scene(pyrt, golden, name, sid):
+    """rt_scene_export_host (generators + builder + reference leaf order on the host) vs the scene dump of the
+    reference's CUDA build. Exact for everything that does not come out of sinf/cosf/tanf (host libm here, CUDA
+    libdevice on the GPU: the `-m gpu` test is bit-exact); those fields within 4 ulps."""
+    g = golden(name)
+    td = texture_dir()
+    for t in NEEDS_TEX.get(sid, []):
+        if td is None or not os.path.exists(os.path.join(td, t + ".ppm")):
+            pytest.skip("decoded texture %s.ppm not present" % t)
+    ref = pyrt.SD(g["sd"].tobytes())
+    mine, rank = pyrt.export_host(sid, int(g["nx"]), int(g["ny"]), texture_dir=td)
+    assert len(mine.top) == len(ref.top) and len(mine.obj) == len(ref.obj)
+    inv = np.argsort(rank)
+    trig = sid in (7, 8)  # rotate_y instances: sin/cos in the object, boxes derived from them
+    for pos in range(len(ref.top)):
+        a, b = ref.obj_key(int(ref.top[pos])), mine.obj_key(int(mine.top[inv[pos]]))
+        assert a == b or (trig and _fkey_close(a, b, 64)), "leaf %d" % pos
+    for n in pyrt.CAM_DT.names:
+        a, b = np.atleast_1d(ref.cam[n]), np.atleast_1d(mine.cam[n])
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-6), n  # camera goes through tanf
+
+
+def test_oracle_leaf_order_equals_host_leaf_order(pyrt, built):
+    """Two independent restatements of the reference BVH constructor's ordering (bvh.cuh:46-81)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    for sid, gh in [(1, 0), (7, 0), (5, 0), (1, 20)]:
+        sd, rank = pyrt.export_host(sid, 64, 64, grid_half=gh, texture_dir=texture_dir())
+        o = oracle_py.Oracle(sd.raw.tobytes())
+        assert np.array_equal(o.leaf_order(), rank), sid
+
+
+def test_ppm_writer_matches_reference_format(pyrt, tmp_path):
+    """main.cu:1212-1221: 'P3\\n{nx} {ny}\\n255\\n', rows j = ny-1..0, int(255.99f*c) per channel, no clamp."""
+    rng = np.random.default_rng(1)
+    fb = (rng.random((5, 7, 3), dtype=np.float32) * 1.3).astype(np.float32)
+    fb[0, 0] = [15.0 ** (1 / 2.2), 0.0, 1.0]  # an emitter: values above 255 are printed as they are
+    p = str(tmp_path / "o.ppm")
+    n = pyrt.write_ppm(p, fb)
+    txt = open(p).read()
+    assert n == len(txt)
+    lines = txt.split("\n")
+    assert lines[0] == "P3" and lines[1] == "7 5" and lines[2] == "255"
+    want = []
+    for j in range(4, -1, -1):
+        for i in range(7):
+            c = fb[j, i]
+            want.append("%d %d %d" % tuple(int(np.float32(255.99) * np.float32(x)) for x in c))
+    assert lines[3:3 + 35] == want
+    assert lines[3 + 28] == "%d 0 255" % int(np.float32(255.99) * np.float32(15.0 ** (1 / 2.2)))  # pixel (0,0) is on the last row
+    # bouncing_spheres prints with a DOUBLE 255.99 (main.cu:722-724)
+    pyrt.write_ppm(p, fb, double_scale=True)
+    l2 = open(p).read().split("\n")
+    c = fb[4, 0]
+    assert l2[3] == "%d %d %d" % tuple(int(255.99 * float(x)) for x in c)
+    assert np.array_equal(pyrt.to_8bit(fb), (np.float32(255.99) * fb).astype(np.int32))
+
+
+def test_partition_arithmetic():
+    from pyrt import dist
+    for ny in (1, 7, 225, 800):
+        for world in (1, 2, 3, 8):
+            rows = [dist.rows_of_rank(ny, r, world) for r in range(world)]
+            assert sorted(sum(rows, [])) == list(range(ny))
+            assert [len(x) for x in rows] == [dist.rows_local(ny, r, world) for r in range(world)]
+    for spp in (1, 10, 1000, 10007):
+        for world in (1, 2, 8):
+            shares = [dist.sample_share(spp, r, world) for r in range(world)]
+            assert shares[0][0] == 0 and shares[-1][1] == spp
+            assert all(shares[i][1] == shares[i + 1][0] for i in range(world - 1))
+    parts = [np.arange(12).reshape(4, 3)[r::3] for r in range(3)]
+    assert np.array_equal(dist.assemble_rows(parts, 4), np.arange(12).reshape(4, 3))
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(pkg)r)
+import numpy as np, torch, torch.distributed as td
+from pyrt import dist
+world, rank, local = dist.init_process_group("gloo")
+assert world == 2 and td.get_backend() == "gloo"
+ny, nx = 9, 5
+full = torch.arange(ny * nx * 3, dtype=torch.float32).view(ny, nx, 3)
+# tile split: each rank holds its scanlines; rank 0 must end up with the whole image
+mine = full[rank::world].contiguous()
+assert mine.shape[0] == dist.rows_local(ny, rank, world)
+got = dist.gather_rows_to_root(mine, ny)
+if rank == 0:
+    assert torch.equal(got, full)
+else:
+    assert got is None
+# spp split: per-rank linear sums reduced to rank 0
+base, end = dist.sample_share(10, rank, world)
+acc = torch.full((ny * nx * 3,), float(end - base))
+dist.reduce_sum_to_root(acc)
+if rank == 0:
+    assert torch.all(acc == 10.0)
+td.barrier()
+td.destroy_process_group()
+print("rank %%d ok" %% rank)
+'''
+
+
+def test_multi_rank_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"pkg": PKG})
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: ranks other than 0 exit 0 without work (the driver launches it under torchrun)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], env=dict(os.environ, RANK="1", WORLD_SIZE="2"), stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == ""
