@@ -146,8 +146,18 @@ static bool tex_needs_uv(const SceneDesc& sd, int t, int depth = 0) {
   return false;
 }
 
-static int queue_of(int mat_kind) {
-  switch (mat_kind) {
+static bool tex_procedural(const SceneDesc& sd, int t, int depth = 0) {
+  if (t < 0 || depth > 8) return false;
+  const rt_texture_desc& d = sd.tex[t];
+  if (d.kind == RT_TEX_NOISE || d.kind == RT_TEX_NOODLE || d.kind == RT_TEX_FELT) return true;
+  if (d.kind == RT_TEX_CHECKER) return tex_procedural(sd, d.even, depth + 1) || tex_procedural(sd, d.odd, depth + 1);
+  if (d.kind == RT_TEX_UV_OFFSET) return tex_procedural(sd, d.even, depth + 1);
+  return false;
+}
+
+static int queue_of(const SceneDesc& sd, const rt_material_desc& m) {
+  if ((m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_ISOTROPIC) && tex_procedural(sd, m.tex)) return Q_PROCEDURAL;
+  switch (m.kind) {
     case RT_MAT_LAMBERTIAN: return Q_LAMBERTIAN;
     case RT_MAT_METAL: return Q_METAL;
     case RT_MAT_DIELECTRIC: return Q_DIELECTRIC;
@@ -171,7 +181,7 @@ static int upload_scene(rt_scene* s) {
     const int mat = sd.obj[mid].mat;
     if (mat < 0 || mat >= (int)sd.mat.size()) return fail("upload_scene: top-level object without a material");
     tlp[k].mat = mat;
-    tlp[k].queue = queue_of(sd.mat[mat].kind);
+    tlp[k].queue = queue_of(sd, sd.mat[mat]);
     tlp[k].rank = s->rank[k];
     refs[k] = tlp[k].ref;
     for (int a = 0; a < 3; ++a) { boxes[k].mn[a] = o.box_min[a]; boxes[k].mx[a] = o.box_max[a]; }

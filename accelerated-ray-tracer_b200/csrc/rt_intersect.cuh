@@ -13,7 +13,7 @@
 namespace rt {
 
 struct Ray { V3 o, d; float tm; };
-struct Rec { float t; V3 p, n; float u, v; };
+struct Rec { float t; V3 p, n; float u, v; int face; };  // face: which of a box's six quads was hit
 
 // ---- sphere (sphere.cuh:51-89) ----
 // T-only form used by traversal: returns the accepted root in (tmin, tmax) exclusive, like the reference.
@@ -87,8 +87,9 @@ RT_D bool box_hit(const DQuad* faces, const Ray& r, float tmin, float tmax, floa
 
 // ---- instance wrappers + leaves: generic hit of a non-medium geometry ref ----
 #define RT_MAX_XFORM 4
+// known_face >= 0 (shading): the box face k_trace found; only that quad is intersected again.
 template <bool FULL>
-RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax, bool want_uv, Rec& rec) {
+RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax, bool want_uv, Rec& rec, int known_face = -1) {
   uint32_t chain[RT_MAX_XFORM];
   V3 dir_in[RT_MAX_XFORM];  // ray direction as each rotate_y saw it (for its normal flip)
   int n = 0;
@@ -124,8 +125,11 @@ RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax,
     if (FULL) quad_fill(q, r, t, a, b, rec);
   } else if (ty == G_BOX) {
     float t, a, b; int face = 0;
-    if (!box_hit(S.quads + ix, r, tmin, tmax, t, face, a, b)) return false;
-    rec.t = t;
+    if (FULL && known_face >= 0) {
+      face = known_face;
+      if (!quad_hit(S.quads[ix + face], r, tmin, tmax, t, a, b)) return false;
+    } else if (!box_hit(S.quads + ix, r, tmin, tmax, t, face, a, b)) return false;
+    rec.t = t; rec.face = face;
     if (FULL) quad_fill(S.quads[ix + face], r, t, a, b, rec);
   } else {
     return false;
@@ -221,21 +225,21 @@ RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
 #ifndef RT_NODE_MIN
 #define RT_NODE_MIN 12     // leaf phase starts when fewer lanes than this can still expand a node
 #endif
-struct Hit { float t; int tlp; };
+struct Hit { float t; int tlp; int face; };
 
-RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, Hit& best) {
-  if (t < best.t || best.tlp < 0) { best.t = t; best.tlp = (int)tlp; return; }
+RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int face, Hit& best) {
+  if (t < best.t || best.tlp < 0) { best.t = t; best.tlp = (int)tlp; best.face = face; return; }
   // exact tie (t == best.t; only inclusive tests get here): order semantics of bvh_node::hit
   const int rn = S.tlp[tlp].rank, rb = S.tlp[best.tlp].rank;
   const bool take = (rn > rb) ? ref_inclusive(S, ref) : !ref_inclusive(S, S.tlp[best.tlp].ref);
-  if (take) { best.t = t; best.tlp = (int)tlp; }
+  if (take) { best.t = t; best.tlp = (int)tlp; best.face = face; }
 }
 
 #define RT_CSWAP(a, b) do { if (tn[b] < tn[a]) { float tf_ = tn[a]; tn[a] = tn[b]; tn[b] = tf_; \
   uint32_t tu_ = cr[a]; cr[a] = cr[b]; cr[b] = tu_; tu_ = ct[a]; ct[a] = ct[b]; ct[b] = tu_; } } while (0)
 
 RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
-  Hit best; best.t = tmax0; best.tlp = -1;
+  Hit best; best.t = tmax0; best.tlp = -1; best.face = 0;
   const float ix = frcp(r.d.x), iy = frcp(r.d.y), iz = frcp(r.d.z);  // 1.0f / direction, aabb.cuh:48
   const bool nx = ix < 0.0f, ny = iy < 0.0f, nz = iz < 0.0f;
   uint32_t stack[RT_STACK];  // interior nodes only
@@ -300,7 +304,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
       for (int k = 0; k < nmax; ++k) {
         if (k < nl && ref_type(lq_ref[k]) == G_SPHERE && lq_tn[k] < best.t) {
           float t; V3 cc;
-          if (sphere_t(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, best);
+          if (sphere_t(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
         }
       }
       // quads, boxes, instances
@@ -310,8 +314,8 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
           if (k < nl) {
             const uint32_t ty = ref_type(lq_ref[k]);
             if (ty != G_SPHERE && ty != G_MEDIUM && lq_tn[k] < best.t) {
-              Rec rec;
-              if (geom_hit<false>(S, lq_ref[k], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[k], lq_tlp[k], rec.t, best);
+              Rec rec; rec.face = 0;
+              if (geom_hit<false>(S, lq_ref[k], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[k], lq_tlp[k], rec.t, rec.face, best);
             }
           }
         }
@@ -322,7 +326,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
         for (int k = 0; k < nmax; ++k) {
           if (k < nl && ref_type(lq_ref[k]) == G_MEDIUM && lq_tn[k] < best.t) {
             float t;
-            if (medium_hit(S, S.media[ref_index(lq_ref[k])], r, tmin, best.t, t)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, best);
+            if (medium_hit(S, S.media[ref_index(lq_ref[k])], r, tmin, best.t, t)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
           }
         }
       }

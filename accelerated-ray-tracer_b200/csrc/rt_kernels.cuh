@@ -30,7 +30,7 @@ namespace rt {
 struct PathArrays {
   float4* ray_o;   // origin.xyz, time
   float4* ray_d;   // direction.xyz, -
-  float2* hit;     // t, top-level object index (int bits; -1 = miss)
+  float2* hit;     // t, (box face << 28 | top-level object index) as int bits; -1 = miss
   float4* thr;     // throughput.rgb, bounce (int bits)
   float4* rad;     // radiance.rgb of the current sample, sample number (int bits)
   float4* col;     // reference-RNG mode: float sum of the pixel's finished samples
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, RenderParams P, PathArr
   const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
   int q = -1;
   if (active) {
-    A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp));
+    A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp < 0 ? -1 : (h.tlp | (h.face << 28))));
     q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
   }
   // bin by material class: one warp-aggregated atomic per class present in the warp
@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, RenderParams P, PathArr
       sample_done = true;
     } else {
       const float2 hh = A.hit[slot];
-      const int tlp = __float_as_int(hh.y);
+      const int packed = __float_as_int(hh.y);
+      const int tlp = packed & 0x0FFFFFFF, face = packed >> 28;
       const DTlp T = S.tlp[tlp];
       const DMat m = S.mats[T.mat];
       Rec rec;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, RenderParams P, PathArr
         rec.n = v3(1, 0, 0);
         rec.u = rec.v = 0.f;
       } else {
-        geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec);
+        geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec, face);
       }
       if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
         const V3 e = material_emitted(S, m, rec);

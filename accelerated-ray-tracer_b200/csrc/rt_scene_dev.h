@@ -61,7 +61,9 @@ struct DImage {
 };
 
 // Shade-queue classes: what the trace kernel sorts paths by.
-enum QueueId : int { Q_MISS = 0, Q_LIGHT = 1, Q_LAMBERTIAN = 2, Q_METAL = 3, Q_DIELECTRIC = 4, Q_ISOTROPIC = 5, Q_COUNT = 6 };
+// Q_PROCEDURAL: lambertian / isotropic whose texture chain evaluates Perlin noise (marble, noodle, felt): ~20x the
+// instructions of any other shade, so those paths get warps of their own.
+enum QueueId : int { Q_MISS = 0, Q_LIGHT = 1, Q_LAMBERTIAN = 2, Q_METAL = 3, Q_DIELECTRIC = 4, Q_ISOTROPIC = 5, Q_PROCEDURAL = 6, Q_COUNT = 7 };
 
 struct alignas(16) DTlp {     // one per top-level object
   uint32_t ref;               // geometry ref

@@ -33,6 +33,15 @@ def pack(prefix, keep=False):
         fb = np.fromfile(p, dtype=np.float32, offset=12).reshape(ny, nx, 3)
         out["fb"] = fb; out["nx"], out["ny"], out["ns"] = nx, ny, ns
         raw.append(p)
+        # <name>_dsK: keep only the KxK box-downsampled LINEAR radiance (gamma 2.2 undone, averaged): the reference at
+        # nx x ny x ns is, per downsampled pixel, a K*K*ns-sample estimate of the same pixel footprint integral
+        m = __import__("re").search(r"_ds(\d+)$", prefix)
+        if m:
+            K = int(m.group(1))
+            lin = np.maximum(fb, 0).astype(np.float64) ** 2.2
+            out["lin_ds"] = lin.reshape(ny // K, K, nx // K, K, 3).mean(axis=(1, 3)).astype(np.float32)
+            out["ds"] = K
+            del out["fb"]
     if out:
         np.savez_compressed(prefix + ".npz", **out)
         if not keep:
