@@ -72,7 +72,7 @@ struct rt_scene {
   // render state
   cudaStream_t stream = nullptr;
   DBuf<float4> ray_o, ray_d, thr, rad, col; DBuf<float2> hit; DBuf<uint32_t> rng;
-  DBuf<int> list0, list1, queues;
+  DBuf<int> queues, order;
   DBuf<WaveCounters> counters;
   WaveCounters* h_counters = nullptr;  // pinned
   DBuf<float> accum, fb, aov_t; DBuf<int> aov_obj, aov_mat; DBuf<unsigned long long> acc64;
@@ -351,7 +351,7 @@ extern "C" int rt_scene_export_host(const rt_scene_desc* desc, void* buf, size_t
 static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rng, bool aov) {
   if (n_slots > s->slots_cap) {
     CU(s->ray_o.alloc(n_slots)); CU(s->ray_d.alloc(n_slots)); CU(s->thr.alloc(n_slots)); CU(s->rad.alloc(n_slots));
-    CU(s->col.alloc(n_slots)); CU(s->hit.alloc(n_slots)); CU(s->list0.alloc(n_slots)); CU(s->list1.alloc(n_slots));
+    CU(s->col.alloc(n_slots)); CU(s->hit.alloc(n_slots)); CU(s->order.alloc(n_slots + 32 * (Q_COUNT + 1)));
     CU(s->queues.alloc(n_slots * Q_COUNT));
     s->rng.free();
     s->slots_cap = n_slots;
@@ -378,7 +378,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   if (ref_rng && p->split_mode == 1 && world > 1)
     return fail("rt_render: reference-RNG mode cannot split a pixel's samples across ranks (one sequential stream per pixel)");
   RenderParams P; memset(&P, 0, sizeof(P));
-  P.nx = sd.nx; P.ny = sd.ny;
+  P.nx = sd.nx; P.ny = sd.ny; P.inv_nx = 1.0f / (float)sd.nx;
   if (p->split_mode == 1) {  // spp split: all pixels, a share of the samples
     P.rank = 0; P.world = 1; P.rows_local = sd.ny;
     const int base = (int)((long long)spp_total * rank / world), end = (int)((long long)spp_total * (rank + 1) / world);
@@ -407,61 +407,65 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
 
   PathArrays A;
   A.ray_o = s->ray_o.p; A.ray_d = s->ray_d.p; A.hit = s->hit.p; A.thr = s->thr.p; A.rad = s->rad.p; A.col = s->col.p;
-  A.rng = s->rng.p; A.acc64 = s->acc64.p;
+  A.rng = s->rng.p; A.acc64 = s->acc64.p; A.order = s->order.p;
   cudaStream_t st = s->stream;
   cudaEvent_t e0, e1, ev;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU(cudaEventRecord(e0, st));
   {
     WaveCounters init; memset(&init, 0, sizeof(init));
-    init.next_work = (unsigned long long)P.n_slots;  // k_start hands out the first n_slots work items itself
+    init.order_len = P.n_slots;
     *s->h_counters = init;
     CU(cudaMemcpyAsync(s->counters.p, s->h_counters, sizeof(WaveCounters), cudaMemcpyHostToDevice, st));
     if (!ref_rng && n_pix > 0) CU(cudaMemsetAsync(s->acc64.p, 0, 3 * n_pix * sizeof(unsigned long long), st));
   }
-  const int B = 128;
+  const int B = RT_BLOCK;
   int launches = 0, waves = 0, prof_waves = 0;
   double prof_trace_ms = 0.0, prof_shade_ms = 0.0;
   if (P.n_slots > 0 && P.sample_count > 0) {
     const int G = (P.n_slots + B - 1) / B;
-    if (ref_rng) k_start<RNG_REFERENCE><<<G, B, 0, st>>>(s->dscene, P, A, s->list0.p, s->counters.p);
-    else k_start<RNG_PHILOX><<<G, B, 0, st>>>(s->dscene, P, A, s->list0.p, s->counters.p);
+    if (ref_rng) k_init<RNG_REFERENCE><<<G, B, 0, st>>>(P, A);
+    else k_init<RNG_PHILOX><<<G, B, 0, st>>>(P, A);
     ++launches;
-    int bound = P.n_slots;  // the live-ray count never grows: the last known value bounds the grid
+    // Every wave runs k_trace over ALL slots (a slot whose sample ended regenerates there) and k_shade over the
+    // queues that wave filled. The host reads the queue fills back every `batch` waves: a wave that traced no
+    // ray means every slot is dead, i.e. the job is done.
     int batch = 8;
     if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
-    FILE* wlog = nullptr;  // diagnostics: one line per wave (live rays at batch start, k_trace ms, k_shade ms)
+    FILE* wlog = nullptr;  // diagnostics: one line per wave (rays of the wave, k_trace ms, k_shade ms)
     if (p->profile) if (const char* e = getenv("RT_WAVE_LOG")) { wlog = fopen(e, "a"); batch = 1; }
     int parity = 0;
     std::vector<cudaEvent_t> pev;
     if (p->profile) { pev.resize(3 * batch); for (auto& e : pev) CU(cudaEventCreate(&e)); }
-    while (bound > 0) {
+    const int Gs = (P.n_slots + 32 * Q_COUNT + B - 1) / B;
+    bool done = false;
+    while (!done) {
       for (int w = 0; w < batch; ++w) {
-        const int Gt = (bound + B - 1) / B;
-        const int Gs = (bound + 32 * Q_COUNT + B - 1) / B;
-        int* cur = parity ? s->list1.p : s->list0.p;
-        int* nxt = parity ? s->list0.p : s->list1.p;
         if (p->profile) CU(cudaEventRecord(pev[3 * w], st));
-        k_trace<<<Gt, B, 0, st>>>(s->dscene, P, A, cur, s->queues.p, s->counters.p, parity);
+        if (ref_rng) k_trace<RNG_REFERENCE><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
+        else k_trace<RNG_PHILOX><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
         if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], st));
-        if (ref_rng) k_shade<RNG_REFERENCE><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, nxt, s->counters.p, parity);
-        else k_shade<RNG_PHILOX><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, nxt, s->counters.p, parity);
+        if (ref_rng) k_shade<RNG_REFERENCE><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
+        else k_shade<RNG_PHILOX><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
         if (p->profile) CU(cudaEventRecord(pev[3 * w + 2], st));
         parity ^= 1; launches += 2; ++waves;
       }
+      // queue fills of the LAST wave of the batch (k_shade zeroes the other parity for the next k_trace)
       CU(cudaMemcpyAsync(s->h_counters, s->counters.p, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
       CU(cudaEventRecord(ev, st));
       CU(cudaEventSynchronize(ev));
+      int last = 0;
+      for (int k = 0; k < Q_COUNT; ++k) last += s->h_counters->n_queue[parity ^ 1][k];
+      done = last == 0;
       if (p->profile) {
         for (int w = 0; w < batch; ++w) {
           float a = 0.f, b = 0.f;
           CU(cudaEventElapsedTime(&a, pev[3 * w], pev[3 * w + 1]));
           CU(cudaEventElapsedTime(&b, pev[3 * w + 1], pev[3 * w + 2]));
           prof_trace_ms += a; prof_shade_ms += b; ++prof_waves;
-          if (wlog) fprintf(wlog, "%d %d %.4f %.4f\n", prof_waves, bound, a, b);
+          if (wlog) fprintf(wlog, "%d %d %.4f %.4f\n", prof_waves, last, a, b);
         }
       }
-      bound = s->h_counters->n_active[parity];
     }
     for (auto& e : pev) cudaEventDestroy(e);
     if (wlog) fclose(wlog);
@@ -499,6 +503,14 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   if (R.stack_overflow) return fail("rt_render: BVH traversal stack overflow (RT_STACK too small for this scene)");
   return 0;
 }
+
+#ifdef RT_STATS
+extern "C" int rt_debug_stats(unsigned long long* out8, int reset) {
+  CU(cudaMemcpyFromSymbol(out8, rt::g_stats, 8 * sizeof(unsigned long long)));
+  if (reset) { unsigned long long z[8] = {0}; CU(cudaMemcpyToSymbol(rt::g_stats, z, sizeof(z))); }
+  return 0;
+}
+#endif
 
 extern "C" int rt_render_stats_get(rt_scene* s, rt_render_stats* out) {
   if (!s || !out) return fail("rt_render_stats_get: null argument");

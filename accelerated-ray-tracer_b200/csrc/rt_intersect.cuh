@@ -226,6 +226,12 @@ RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
 #define RT_NODE_MIN 12     // leaf phase starts when fewer lanes than this can still expand a node
 #endif
 struct Hit { float t; int tlp; int face; };
+#ifdef RT_STATS  // diagnostics build only (tools/): per-ray work counters
+__device__ unsigned long long g_stats[8];  // 0 node expansions, 1 sphere tests, 2 geom tests, 3 medium tests, 4 node phases, 5 leaf phases, 6 leaves queued, 7 leaves culled
+#define RT_COUNT(i, n) atomicAdd(&g_stats[i], (unsigned long long)(n))
+#else
+#define RT_COUNT(i, n) do { } while (0)
+#endif
 
 RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int face, Hit& best) {
   if (t < best.t || best.tlp < 0) { best.t = t; best.tlp = (int)tlp; best.face = face; return; }
@@ -255,7 +261,9 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
     if ((mexp | mleaf) == 0u) break;
     if (mleaf == 0u || __popc(mexp) >= RT_NODE_MIN) {
       // ---------------- node phase ----------------
+      if ((threadIdx.x & 31) == 0) RT_COUNT(4, 1);
       if (can) {
+        RT_COUNT(0, 1);
         const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
         const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
         const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
@@ -299,11 +307,14 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
       }
     } else {
       // ---------------- leaf phase ----------------
+      if ((threadIdx.x & 31) == 0) RT_COUNT(5, 1);
+      RT_COUNT(6, nl);
       const int nmax = __reduce_max_sync(0xFFFFFFFFu, nl);
       // spheres
       for (int k = 0; k < nmax; ++k) {
         if (k < nl && ref_type(lq_ref[k]) == G_SPHERE && lq_tn[k] < best.t) {
           float t; V3 cc;
+          RT_COUNT(1, 1);
           if (sphere_t(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
         }
       }
@@ -315,6 +326,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
             const uint32_t ty = ref_type(lq_ref[k]);
             if (ty != G_SPHERE && ty != G_MEDIUM && lq_tn[k] < best.t) {
               Rec rec; rec.face = 0;
+              RT_COUNT(2, 1);
               if (geom_hit<false>(S, lq_ref[k], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[k], lq_tlp[k], rec.t, rec.face, best);
             }
           }
@@ -326,6 +338,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
         for (int k = 0; k < nmax; ++k) {
           if (k < nl && ref_type(lq_ref[k]) == G_MEDIUM && lq_tn[k] < best.t) {
             float t;
+            RT_COUNT(3, 1);
             if (medium_hit(S, S.media[ref_index(lq_ref[k])], r, tmin, best.t, t)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
           }
         }

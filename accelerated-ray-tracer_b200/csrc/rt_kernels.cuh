@@ -4,22 +4,22 @@
 // through virtual calls and device recursion (render/color, main.cu:44-133). Here the same
 // integrator runs as waves over a pool of path slots kept in SoA arrays in HBM/L2:
 //
-//   k_start    every slot draws its first camera ray                         (main.cu:119-123)
-//   k_trace    closest hit of every live ray over the 4-wide BVH; paths are binned by the hit
-//              material class into shade queues (warp-aggregated atomics)   (main.cu:57; bvh.cuh:95)
-//   k_shade    one material class per warp: miss/background, emission, scatter, throughput;
-//              finished samples are folded into the slot's sum and the slot draws its next
-//              camera ray in place (path regeneration); survivors are compacted into the
-//              next wave's ray list                                          (main.cu:58-83, 119-125)
-//   k_resolve  per pixel: sum the slot partials, scale by 1/ns, gamma        (main.cu:128-132)
+//   k_init     slot state: "needs a sample"; reference-RNG mode: XORWOW seeding      (render_init, main.cu:96-105)
+//   k_trace    one thread per SLOT (coalesced state access, no ray lists): a slot whose sample has ended
+//              takes its next camera sample here (path regeneration, main.cu:119-123), then the closest
+//              hit over the 4-wide BVH; paths are binned by the hit material class into shade queues
+//              (per-block aggregation, one global atomic per class per block)        (main.cu:57; bvh.cuh:95)
+//   k_shade    one material class per warp: miss/background, emission, scatter, throughput; a finished
+//              sample is added to its pixel and the slot is flagged "needs a sample"  (main.cu:58-83, 124)
+//   k_accumulate / k_resolve   sums -> linear accumulation buffer -> 1/ns, gamma     (main.cu:128-132)
 //   k_aov      primary-hit object/material id + t for the centre ray of every pixel
 //
 // Philox mode (production): a slot is a worker. Work item w = sample * n_local_pixels + local_pixel is
-// handed out by one 64-bit counter (warp-aggregated), so every slot stays busy until the whole job is
-// done no matter how unevenly path lengths are spread over the image (on the Book-2 final scene the
-// pixel-bound scheme ran at 11% mean slot occupancy). A finished sample is added to its pixel with
-// 64-bit FIXED-POINT atomics (2^-32 resolution): integer sums do not depend on the order of arrival,
-// so the image is bit-reproducible and identical under any tile split.
+// handed out by one 64-bit counter (one atomic per block, at the head of k_trace), so every slot stays
+// busy until the whole job is done no matter how unevenly path lengths are spread over the image (on
+// the Book-2 final scene a pixel-bound scheme ran at 11% mean slot occupancy). A finished sample is
+// added to its pixel with 64-bit FIXED-POINT atomics (2^-32 resolution): integer sums do not depend on
+// the order of arrival, so the image is bit-reproducible and identical under any tile split.
 // Reference-RNG mode (validation): a slot IS a pixel and consumes that pixel's XORWOW stream in exactly
 // the reference's order, samples one after the other, summed in float like `col += color(...)`.
 #pragma once
@@ -29,18 +29,19 @@ namespace rt {
 
 struct PathArrays {
   float4* ray_o;   // origin.xyz, time
-  float4* ray_d;   // direction.xyz, -
+  float4* ray_d;   // direction.xyz, local pixel (int bits)
   float2* hit;     // t, (box face << 28 | top-level object index) as int bits; -1 = miss
-  float4* thr;     // throughput.rgb, bounce (int bits)
+  float4* thr;     // throughput.rgb, bounce (int bits); bounce = SLOT_NEEDS_SAMPLE / SLOT_DEAD are slot states
   float4* rad;     // radiance.rgb of the current sample, sample number (int bits)
   float4* col;     // reference-RNG mode: float sum of the pixel's finished samples
   uint32_t* rng;   // reference-RNG mode: 6 words per slot, SoA [6][n_slots]
   unsigned long long* acc64;  // Philox mode: per local pixel 3 x fixed-point (2^-32) radiance sums
+  int* order;      // k_trace thread -> slot: the previous wave's shade-queue layout (-1 = hole), see k_shade
 };
 
 struct WaveCounters {
-  int n_active[2];             // live rays in list[parity]
-  int n_queue[2][Q_COUNT + 2]; // shade queue fill, by wave parity
+  int n_queue[2][Q_COUNT + 1]; // shade queue fill, by wave parity (their sum = rays traced in that wave)
+  int order_len;               // entries of PathArrays::order in use
   unsigned long long rays;     // closest-hit queries issued (= the reference's bounce-loop iterations)
   unsigned long long samples;  // finished samples
   unsigned int overflow;       // traversal stack overflow flag (must stay 0)
@@ -50,6 +51,7 @@ struct WaveCounters {
 
 struct RenderParams {
   int nx, ny;            // full image
+  float inv_nx;          // 1.0f / nx
   int rows_local;        // scanlines owned by this rank (tile split: j = lr * world + rank)
   int rank, world;
   int n_slots;           // path slots in flight (reference-RNG mode: one per local pixel)
@@ -63,13 +65,18 @@ struct RenderParams {
 };
 
 enum RngMode : int { RNG_PHILOX = 0, RNG_REFERENCE = 1 };
+enum SlotState : int { SLOT_NEEDS_SAMPLE = -1, SLOT_DEAD = -2 };
 
 struct SlotInfo { int lpix, i, j, pix; };
 RT_D SlotInfo pixel_info(const RenderParams& P, int lpix) {
   SlotInfo s;
   s.lpix = lpix;
-  const int lr = s.lpix / P.nx;
-  s.i = s.lpix - lr * P.nx;
+  // lpix / nx without the ~25-instruction integer divide: float estimate (off by at most one for any image with
+  // fewer than 2^22 rows) plus one correction step
+  int lr = __float2int_rz(__fmul_rz(__int2float_rz(lpix), P.inv_nx));
+  int i = lpix - lr * P.nx;
+  if (i < 0) { --lr; i += P.nx; } else if (i >= P.nx) { ++lr; i -= P.nx; }
+  s.i = i;
   s.j = lr * P.world + P.rank;
   s.pix = s.j * P.nx + s.i;  // the reference's pixel_index (main.cu:115)
   return s;
@@ -100,124 +107,173 @@ RT_D void rng_store(const Xorwow& g, const PathArrays& A, const RenderParams& P,
 
 // New camera sample for a slot (main.cu:121-123): jitter, lens, shutter time; throughput 1, radiance 0.
 template <class RNG>
-RT_D void start_sample(const DScene& S, const RenderParams& P, const PathArrays& A, int slot, const SlotInfo& si, int sample, RNG& g) {
+RT_D Ray start_sample(const DScene& S, const RenderParams& P, const PathArrays& A, int slot, const SlotInfo& si, int sample, RNG& g) {
   // ray_d.w carries the slot's local pixel, rad.w its sample number
   const float u = fdiv(fadd((float)si.i, g.uniform()), (float)P.nx);
   const float v = fdiv(fadd((float)si.j, g.uniform()), (float)P.ny);
-  Ray r = camera_get_ray(S.cam, u, v, g);
+  const Ray r = camera_get_ray(S.cam, u, v, g);
   A.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
   A.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(si.lpix));
   A.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
   A.rad[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(sample));
+  return r;
 }
 
-// Warp-aggregated append: lanes with `pred` get consecutive positions in a global list.
-RT_D int warp_append(int* counter, bool pred) {
-  const unsigned m = __ballot_sync(__activemask(), pred);
-  if (!pred) return -1;
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(counter, __popc(m));
-  base = __shfl_sync(m, base, leader);
-  return base + __popc(m & ((1u << lane) - 1u));
+// Block-aggregated reservation: EVERY thread of the block calls it; threads with `pred` get consecutive
+// positions starting at a base taken with ONE global atomic per block (a wave of 1 Mi rays appends to a single
+// counter: one atomic per warp serialised 32 Ki same-address atomics in L2 and cost ~40% of k_shade, profiles/r01).
+#define RT_BLOCK 256
+#ifndef RT_SHADE_MINB
+#define RT_SHADE_MINB 3   // resident blocks per SM the shade kernel is compiled for (register cap 65536 / (256 * MINB))
+#endif
+#define RT_WARPS (RT_BLOCK / 32)
+template <class T>
+RT_D T block_reserve(T* counter, bool pred, int* s_cnt /*[RT_WARPS]*/, T* s_base) {
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_cnt[warp] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < RT_WARPS; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+    *s_base = tot > 0 ? atomicAdd(counter, (T)tot) : (T)0;
+  }
+  __syncthreads();
+  const T pos = *s_base + (T)(s_cnt[warp] + __popc(m & ((1u << lane) - 1u)));
+  __syncthreads();  // s_cnt / s_base may be reused by the next call
+  return pos;
 }
 
-// Warp-aggregated grab of consecutive work items: lanes with `pred` get w, w+1, ... in lane order.
-RT_D unsigned long long warp_grab(unsigned long long* counter, bool pred) {
-  const unsigned m = __ballot_sync(__activemask(), pred);
-  if (!pred) return ~0ull;
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  unsigned long long base = 0;
-  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
-  base = __shfl_sync(m, base, leader);
-  return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-}
 #define RT_FIXED_ONE 4294967296.0f  /* 2^32 */
 RT_D void fixed_add(unsigned long long* acc, float v) {
   atomicAdd(acc, (unsigned long long)__float2ll_rn(v * RT_FIXED_ONE));  // two's complement: negative values add correctly
 }
 RT_D void work_to_pixel_sample(const RenderParams& P, unsigned long long w, int& lpix, int& sample) {
-  const unsigned long long npl = (unsigned long long)(P.rows_local * P.nx);
-  const unsigned long long s = w / npl;
-  lpix = (int)(w - s * npl);
-  sample = P.sample_base + (int)s;
+  if (P.work_total <= 0xFFFFFFFFll) {  // the usual case: 32-bit divide
+    const unsigned npl = (unsigned)(P.rows_local * P.nx), w32 = (unsigned)w;
+    const unsigned s = w32 / npl;
+    lpix = (int)(w32 - s * npl);
+    sample = P.sample_base + (int)s;
+  } else {
+    const unsigned long long npl = (unsigned long long)(P.rows_local * P.nx);
+    const unsigned long long s = w / npl;
+    lpix = (int)(w - s * npl);
+    sample = P.sample_base + (int)s;
+  }
 }
 
+// Slot state before the first wave: every slot needs a sample. Reference-RNG mode also seeds the pixel's stream
+// (render_init, main.cu:104) and zeroes its float sum; rad.w = the sample number BEFORE the first one.
 template <int MODE>
-__global__ void __launch_bounds__(128) k_start(DScene S, RenderParams P, PathArrays A, int* list0, WaveCounters* C) {
+__global__ void __launch_bounds__(RT_BLOCK) k_init(RenderParams P, PathArrays A) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= P.n_slots) return;
-  typename RngOf<MODE>::type g;
-  bool live;
+  A.order[slot] = slot;  // first wave: identity (the host sets order_len = n_slots)
+  A.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)SLOT_NEEDS_SAMPLE));
+  A.rad[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(P.sample_base - 1));
   if constexpr (MODE == RNG_REFERENCE) {
     const SlotInfo si = pixel_info(P, slot);  // slot == local pixel
     A.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    g.init((unsigned long long)(long long)(1984 + si.pix));  // render_init, main.cu:104
-    live = P.sample_count > 0;
-    if (live) start_sample(S, P, A, slot, si, P.sample_base, g);
+    Xorwow g;
+    g.init((unsigned long long)(long long)(1984 + si.pix));
     rng_store(g, A, P, slot);
-  } else {
-    live = (long long)slot < P.work_total;  // the first n_slots work items; the counter starts behind them
-    if (live) {
-      int lpix, sample;
-      work_to_pixel_sample(P, (unsigned long long)slot, lpix, sample);
-      const SlotInfo si = pixel_info(P, lpix);
-      rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-      start_sample(S, P, A, slot, si, sample, g);
-    }
   }
-  const int pos = warp_append(&C->n_active[0], live);
-  if (live) list0[pos] = slot;
 }
 
-__global__ void __launch_bounds__(128) k_trace(DScene S, RenderParams P, PathArrays A, const int* __restrict__ list,
-                                               int* __restrict__ queues, WaveCounters* C, int parity) {
-  const int n = C->n_active[parity];
+template <int MODE>
+__global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RenderParams P, PathArrays A, int* __restrict__ queues,
+                                                    WaveCounters* C, int parity) {
+  __shared__ int s_cnt[RT_WARPS];
+  __shared__ unsigned long long s_wbase;
+  __shared__ int s_q[RT_WARPS][Q_COUNT];
+  __shared__ int s_qbase[Q_COUNT];
+  // Thread -> slot through the previous wave's queue layout: paths that hit the same material class sit next to
+  // each other, and the primary rays regenerated behind the miss / light queues come out in pixel order, which
+  // keeps warps far more coherent than slot order (measured: 0.32 ms vs 0.53 ms per 1 Mi-ray wave on C4).
+  // No early exit: closest_hit is warp-wide, the binning block-wide.
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    C->n_active[parity ^ 1] = 0;  // the shade kernel of this wave appends here
-    C->rays += (unsigned long long)n;
-  }
-  if ((gid & ~31) >= n) return;  // whole warps only: closest_hit is a warp-wide routine
-  const bool active = gid < n;
-  const int slot = active ? list[gid] : 0;
+  int slot = -1;
+  if (gid < C->order_len) slot = A.order[gid];
+  const bool in_range = slot >= 0;
+  int state = SLOT_DEAD;
+  if (in_range) state = __float_as_int(A.thr[slot].w);
+  bool active = state >= 0;
   Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
-  if (active) {
+  // ---- path regeneration (main.cu:119-123): a slot whose sample has ended takes the next one ----
+  const bool need = state == SLOT_NEEDS_SAMPLE;
+  if constexpr (MODE == RNG_PHILOX) {
+    const unsigned long long w = block_reserve(&C->next_work, need, s_cnt, &s_wbase);
+    if (need) {
+      if (w < (unsigned long long)P.work_total) {
+        int lpix, sample;
+        work_to_pixel_sample(P, w, lpix, sample);
+        const SlotInfo si = pixel_info(P, lpix);
+        Philox g;
+        rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
+        r = start_sample(S, P, A, slot, si, sample, g);
+        active = true;
+      } else {
+        A.thr[slot].w = __int_as_float((int)SLOT_DEAD);
+      }
+    }
+  } else {
+    if (need) {
+      const int sample = __float_as_int(A.rad[slot].w) + 1;
+      if (sample < P.sample_base + P.sample_count) {
+        const SlotInfo si = pixel_info(P, slot);
+        Xorwow g;
+        rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
+        r = start_sample(S, P, A, slot, si, sample, g);
+        rng_store(g, A, P, slot);
+        active = true;
+      } else {
+        A.thr[slot].w = __int_as_float((int)SLOT_DEAD);
+      }
+    }
+  }
+  if (active && !need) {
     const float4 o = A.ray_o[slot], d = A.ray_d[slot];
     r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
   }
+  // ---- closest hit (main.cu:57) ----
   const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
   int q = -1;
   if (active) {
     A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp < 0 ? -1 : (h.tlp | (h.face << 28))));
     q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
   }
-  // bin by material class: one warp-aggregated atomic per class present in the warp
-  const unsigned peers = __match_any_sync(__activemask(), q);
-  if (active) {
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&C->n_queue[parity][q], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    queues[(size_t)q * P.n_slots + base + __popc(peers & ((1u << lane) - 1u))] = slot;
+  // ---- bin by material class: per-warp counts per class in shared memory, ONE global atomic per class per block ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < Q_COUNT) s_q[warp][lane] = 0;
+  __syncwarp();
+  const unsigned peers = __match_any_sync(0xFFFFFFFFu, q);
+  if (q >= 0 && lane == __ffs(peers) - 1) s_q[warp][q] = __popc(peers);
+  __syncthreads();
+  if (threadIdx.x < Q_COUNT) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < RT_WARPS; ++w) { const int c = s_q[w][threadIdx.x]; s_q[w][threadIdx.x] = tot; tot += c; }
+    s_qbase[threadIdx.x] = tot > 0 ? atomicAdd(&C->n_queue[parity][threadIdx.x], tot) : 0;
   }
+  __syncthreads();
+  if (q >= 0) queues[(size_t)q * P.n_slots + s_qbase[q] + s_q[warp][q] + __popc(peers & ((1u << lane) - 1u))] = slot;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128) k_shade(DScene S, RenderParams P, PathArrays A, const int* __restrict__ queues,
-                                               int* __restrict__ next_list, WaveCounters* C, int parity) {
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, RenderParams P, PathArrays A, const int* __restrict__ queues,
+                                                                   WaveCounters* C, int parity) {
   // thread -> (queue, position): queues are laid end to end, each padded to a whole warp
   int cnt[Q_COUNT];
-  int total = 0;
+  int total = 0, rays = 0;
 #pragma unroll
-  for (int k = 0; k < Q_COUNT; ++k) { cnt[k] = C->n_queue[parity][k]; total += (cnt[k] + 31) & ~31; }
+  for (int k = 0; k < Q_COUNT; ++k) { cnt[k] = C->n_queue[parity][k]; total += (cnt[k] + 31) & ~31; rays += cnt[k]; }
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < Q_COUNT; ++k) C->n_queue[parity ^ 1][k] = 0;  // next wave's trace fills these
+    C->rays += (unsigned long long)rays;
+    C->order_len = total;  // the next k_trace walks this wave's queue layout
   }
   if (gid >= total) return;
   int q = 0, base = 0, qcount = cnt[0];
@@ -227,107 +283,80 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, RenderParams P, PathArr
     if (q == k && gid >= base + padded) { base += padded; q = k + 1; qcount = cnt[k + 1]; }
   }
   const int pos = gid - base;
-  const bool valid = pos < qcount;
-  bool alive = false, want_work = false;
-  int slot = -1;
-  if (valid) {
-    slot = queues[(size_t)q * P.n_slots + pos];
-    const float4 o = A.ray_o[slot], d = A.ray_d[slot];
-    SlotInfo si = pixel_info(P, __float_as_int(d.w));
-    float4 thr4 = A.thr[slot], rad4 = A.rad[slot];
-    Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
-    V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(rad4.x, rad4.y, rad4.z);
-    int bounce = __float_as_int(thr4.w);
-    int sample = __float_as_int(rad4.w);
-    typename RngOf<MODE>::type g;
-    rng_load<MODE>(g, A, P, slot, si.pix, sample, bounce + 1);
-    bool sample_done;
-    Ray next; next.o = r.o; next.d = r.d; next.tm = r.tm;
-    if (q == Q_MISS) {
-      // main.cu:58-68
-      V3 bg = P.background;
-      if (P.gradient) {
-        const float uy = fdiv(r.d.y, vlen(r.d));
-        const float t = fmul(0.5f, fadd(uy, 1.0f));
-        const float omt = fsub(1.0f, t);
-        bg = v3(ffma(t, 0.5f, omt), ffma(t, 0.7f, omt), fadd(t, omt));
-      }
-      rad = v3(ffma(thr.x, bg.x, rad.x), ffma(thr.y, bg.y, rad.y), ffma(thr.z, bg.z, rad.z));
-      sample_done = true;
-    } else {
-      const float2 hh = A.hit[slot];
-      const int packed = __float_as_int(hh.y);
-      const int tlp = packed & 0x0FFFFFFF, face = packed >> 28;
-      const DTlp T = S.tlp[tlp];
-      const DMat m = S.mats[T.mat];
-      Rec rec;
-      if (ref_type(T.ref) == G_MEDIUM) {  // constant_medium.cuh:58-62
-        rec.t = hh.x;
-        rec.p = vmad(hh.x, r.d, r.o);
-        rec.n = v3(1, 0, 0);
-        rec.u = rec.v = 0.f;
-      } else {
-        geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec, face);
-      }
-      if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
-        const V3 e = material_emitted(S, m, rec);
-        rad = v3(ffma(thr.x, e.x, rad.x), ffma(thr.y, e.y, rad.y), ffma(thr.z, e.z, rad.z));
-      }
-      V3 att;
-      const bool scattered = material_scatter(S, m, r, rec, g, att, next);  // main.cu:76
-      if (scattered) {
-        thr = vmul(thr, att);  // main.cu:82
-        ++bounce;
-      }
-      sample_done = !scattered || bounce >= P.max_depth;
+  if (pos >= qcount) { A.order[gid] = -1; return; }  // warp padding between two queues
+  const int slot = queues[(size_t)q * P.n_slots + pos];
+  A.order[gid] = slot;
+  const float4 o = A.ray_o[slot], d = A.ray_d[slot];
+  const float4 thr4 = A.thr[slot], rad4 = A.rad[slot];
+  const SlotInfo si = pixel_info(P, __float_as_int(d.w));
+  Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+  V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(rad4.x, rad4.y, rad4.z);
+  int bounce = __float_as_int(thr4.w);
+  const int sample = __float_as_int(rad4.w);
+  typename RngOf<MODE>::type g;
+  rng_load<MODE>(g, A, P, slot, si.pix, sample, bounce + 1);
+  bool sample_done;
+  Ray next; next.o = r.o; next.d = r.d; next.tm = r.tm;
+  if (q == Q_MISS) {
+    // main.cu:58-68
+    V3 bg = P.background;
+    if (P.gradient) {
+      const float uy = fdiv(r.d.y, vlen(r.d));
+      const float t = fmul(0.5f, fadd(uy, 1.0f));
+      const float omt = fsub(1.0f, t);
+      bg = v3(ffma(t, 0.5f, omt), ffma(t, 0.7f, omt), fadd(t, omt));
     }
+    rad = v3(ffma(thr.x, bg.x, rad.x), ffma(thr.y, bg.y, rad.y), ffma(thr.z, bg.z, rad.z));
+    sample_done = true;
+  } else {
+    const float2 hh = A.hit[slot];
+    const int packed = __float_as_int(hh.y);
+    const int tlp = packed & 0x0FFFFFFF, face = packed >> 28;
+    const DTlp T = S.tlp[tlp];
+    const DMat m = S.mats[T.mat];
+    Rec rec;
+    if (ref_type(T.ref) == G_MEDIUM) {  // constant_medium.cuh:58-62
+      rec.t = hh.x;
+      rec.p = vmad(hh.x, r.d, r.o);
+      rec.n = v3(1, 0, 0);
+      rec.u = rec.v = 0.f;
+    } else {
+      geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec, face);
+    }
+    if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
+      const V3 e = material_emitted(S, m, rec);
+      rad = v3(ffma(thr.x, e.x, rad.x), ffma(thr.y, e.y, rad.y), ffma(thr.z, e.z, rad.z));
+    }
+    V3 att;
+    const bool scattered = material_scatter(S, m, r, rec, g, att, next);  // main.cu:76
+    if (scattered) {
+      thr = vmul(thr, att);  // main.cu:82
+      ++bounce;
+    }
+    sample_done = !scattered || bounce >= P.max_depth;
+  }
+  if (sample_done) {
     if constexpr (MODE == RNG_REFERENCE) {
-      if (sample_done) {
-        // render: col += color(...) (main.cu:124), then the next sample of this pixel, if any
-        float4 c = A.col[slot];
-        c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
-        A.col[slot] = c;
-        ++sample;
-        if (sample < P.sample_base + P.sample_count) {
-          start_sample(S, P, A, slot, si, sample, g);
-          alive = true;
-        }
-      }
+      // render: col += color(...) (main.cu:124)
+      float4 c = A.col[slot];
+      c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
+      A.col[slot] = c;
     } else {
-      if (sample_done) {
-        if (isfinite(rad.x) && isfinite(rad.y) && isfinite(rad.z)) {
-          unsigned long long* acc = A.acc64 + 3 * (size_t)si.lpix;
-          fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
-        } else {
-          atomicAdd(&C->nonfinite, 1u);
-        }
+      if (isfinite(rad.x) && isfinite(rad.y) && isfinite(rad.z)) {
+        unsigned long long* acc = A.acc64 + 3 * (size_t)si.lpix;
+        fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
+      } else {
+        atomicAdd(&C->nonfinite, 1u);
       }
     }
-    if (!sample_done) {
-      A.ray_o[slot] = make_float4(next.o.x, next.o.y, next.o.z, next.tm);
-      A.ray_d[slot] = make_float4(next.d.x, next.d.y, next.d.z, d.w);
-      A.thr[slot] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce));
-      A.rad[slot] = make_float4(rad.x, rad.y, rad.z, __int_as_float(sample));
-      alive = true;
-    }
-    rng_store(g, A, P, slot);
-    if constexpr (MODE == RNG_PHILOX) want_work = sample_done;
+    A.thr[slot].w = __int_as_float((int)SLOT_NEEDS_SAMPLE);  // k_trace of the next wave regenerates the slot
+  } else {
+    A.ray_o[slot] = make_float4(next.o.x, next.o.y, next.o.z, next.tm);
+    A.ray_d[slot] = make_float4(next.d.x, next.d.y, next.d.z, d.w);
+    A.thr[slot] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce));
+    A.rad[slot] = make_float4(rad.x, rad.y, rad.z, rad4.w);
   }
-  if constexpr (MODE == RNG_PHILOX) {
-    // path regeneration: finished lanes take the next work items (consecutive pixels of one sample number)
-    const unsigned long long w = warp_grab(&C->next_work, want_work);
-    if (want_work && w < (unsigned long long)P.work_total) {
-      int lpix, sample;
-      work_to_pixel_sample(P, w, lpix, sample);
-      const SlotInfo si = pixel_info(P, lpix);
-      Philox g;
-      rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-      start_sample(S, P, A, slot, si, sample, g);
-      alive = true;
-    }
-  }
-  const int np = warp_append(&C->n_active[parity ^ 1], alive);
-  if (alive) next_list[np] = slot;
+  rng_store(g, A, P, slot);
 }
 
 RT_D float apply_gamma(float c, float gamma) {  // main.cu:37-42

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "librt_b200.so")
+LIB_PATH = os.environ.get("RT_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "librt_b200.so")  # RT_LIB: diagnostics builds
 REPO_ROOT = os.path.dirname(os.path.dirname(_HERE))
 
 SCENE_NAMES = {1: "bouncing", 2: "checker", 3: "earth", 4: "perlin", 5: "quads", 6: "simple_light",
