@@ -92,11 +92,11 @@ struct Flattener {
   explicit Flattener(const SceneDesc& s) : sd(s) {}
   static DQuad mkquad(const rt_object_desc& o) {
     DQuad q;
-    q.Qx = o.Q[0]; q.Qy = o.Q[1]; q.Qz = o.Q[2]; q.D = o.D;
-    q.ux = o.u[0]; q.uy = o.u[1]; q.uz = o.u[2]; q.mat = o.mat;
-    q.vx = o.v[0]; q.vy = o.v[1]; q.vz = o.v[2]; q.pad0 = 0;
-    q.wx = o.w[0]; q.wy = o.w[1]; q.wz = o.w[2]; q.pad1 = 0;
-    q.nx = o.n[0]; q.ny = o.n[1]; q.nz = o.n[2]; q.pad2 = 0;
+    q.nx = o.n[0]; q.ny = o.n[1]; q.nz = o.n[2]; q.D = o.D;
+    q.Qx = o.Q[0]; q.Qy = o.Q[1]; q.Qz = o.Q[2]; q.mat = o.mat;
+    q.ux = o.u[0]; q.uy = o.u[1]; q.uz = o.u[2]; q.pad0 = 0;
+    q.vx = o.v[0]; q.vy = o.v[1]; q.vz = o.v[2]; q.pad1 = 0;
+    q.wx = o.w[0]; q.wy = o.w[1]; q.wz = o.w[2]; q.pad2 = 0;
     return q;
   }
   uint32_t flatten(int id) {

@@ -47,19 +47,32 @@ RT_D void sphere_fill(const DSphere& s, const Ray& r, float t, V3 cc, bool want_
 }
 
 // ---- quad (quad.cuh:60-90); bounds inclusive: rejects t < tmin || t > tmax ----
-RT_D bool quad_hit(const DQuad& q, const Ray& r, float tmin, float tmax, float& t_out, float& alpha, float& beta) {
-  V3 n = v3(q.nx, q.ny, q.nz);
-  float denom = vdot(n, r.d);
+// Split in two so that a box can find its candidate face from the six plane distances before it pays for an
+// interior test: quad_plane = lines 61-64, quad_interior = lines 66-70 of the reference's quad::hit.
+RT_D bool quad_plane(const float4 nD, const Ray& r, float tmin, float tmax, float& t_out) {
+  const V3 n = v3(nD.x, nD.y, nD.z);
+  const float denom = vdot(n, r.d);
   if (fabsf(denom) < 1e-8f) return false;
-  float t = fdiv(fsub(q.D, vdot(n, r.o)), denom);
+  const float t = fdiv(fsub(nD.w, vdot(n, r.o)), denom);
   if (t < tmin || t > tmax) return false;
-  V3 P = vmad(t, r.d, r.o);
-  V3 pl = vsub(P, v3(q.Qx, q.Qy, q.Qz));
-  V3 w = v3(q.wx, q.wy, q.wz);
-  float a = vdot(w, vcross(pl, v3(q.vx, q.vy, q.vz)));
-  float b = vdot(w, vcross(v3(q.ux, q.uy, q.uz), pl));
+  t_out = t;
+  return true;
+}
+RT_D bool quad_interior(const DQuad& q, const Ray& r, float t, float& alpha, float& beta) {
+  const V3 P = vmad(t, r.d, r.o);
+  const V3 pl = vsub(P, v3(q.Qx, q.Qy, q.Qz));
+  const V3 w = v3(q.wx, q.wy, q.wz);
+  const float a = vdot(w, vcross(pl, v3(q.vx, q.vy, q.vz)));
+  const float b = vdot(w, vcross(v3(q.ux, q.uy, q.uz), pl));
   if (a < 0.f || a > 1.f || b < 0.f || b > 1.f) return false;
-  t_out = t; alpha = a; beta = b;
+  alpha = a; beta = b;
+  return true;
+}
+RT_D bool quad_hit(const DQuad& q, const Ray& r, float tmin, float tmax, float& t_out, float& alpha, float& beta) {
+  float t;
+  if (!quad_plane(make_float4(q.nx, q.ny, q.nz, q.D), r, tmin, tmax, t)) return false;
+  if (!quad_interior(q, r, t, alpha, beta)) return false;
+  t_out = t;
   return true;
 }
 RT_D void quad_fill(const DQuad& q, const Ray& r, float t, float alpha, float beta, Rec& rec) {
@@ -72,17 +85,32 @@ RT_D void quad_fill(const DQuad& q, const Ray& r, float t, float alpha, float be
 }
 
 // ---- compound6 (quad.cuh:124-139): closest of six faces, later face wins ties ----
+// The reference walks the faces in order with a shrinking t_max; since a face's interior test does not depend on
+// t_max, its answer is the face with the smallest plane distance among those inside [tmin, tmax] whose interior
+// test passes, the LATER face on an exact tie (the interval test is inclusive). Computed here as: six plane
+// distances first (independent loads), then interior tests in ascending-t order until one passes - usually one
+// interior test instead of six.
 RT_D bool box_hit(const DQuad* faces, const Ray& r, float tmin, float tmax, float& t_out, int& face, float& alpha,
                   float& beta) {
-  bool any = false;
-  float closest = tmax;
-#pragma unroll 1
+  float tf[6];
+  unsigned valid = 0;
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
-    float t, a, b;
-    if (quad_hit(faces[i], r, tmin, closest, t, a, b)) { any = true; closest = t; face = i; alpha = a; beta = b; }
+    const float4 nD = __ldg(reinterpret_cast<const float4*>(faces + i));
+    tf[i] = FLT_MAX;
+    if (quad_plane(nD, r, tmin, tmax, tf[i])) valid |= 1u << i;
   }
-  t_out = closest;
-  return any;
+  while (valid) {
+    int bi = -1; float bt = FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if ((valid >> i & 1u) && tf[i] <= bt) { bt = tf[i]; bi = i; }  // <=: the later face wins a tie
+    if (bi < 0) return false;  // only NaN distances left (a ray with a NaN direction)
+    float a, b;
+    if (quad_interior(faces[bi], r, bt, a, b)) { t_out = bt; face = bi; alpha = a; beta = b; return true; }
+    valid &= ~(1u << bi);
+  }
+  return false;
 }
 
 // ---- instance wrappers + leaves: generic hit of a non-medium geometry ref ----
@@ -241,13 +269,11 @@ RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int 
   if (take) { best.t = t; best.tlp = (int)tlp; best.face = face; }
 }
 
-#define RT_CSWAP(a, b) do { if (tn[b] < tn[a]) { float tf_ = tn[a]; tn[a] = tn[b]; tn[b] = tf_; \
-  uint32_t tu_ = cr[a]; cr[a] = cr[b]; cr[b] = tu_; tu_ = ct[a]; ct[a] = ct[b]; ct[b] = tu_; } } while (0)
-
 RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
   Hit best; best.t = tmax0; best.tlp = -1; best.face = 0;
   const float ix = frcp(r.d.x), iy = frcp(r.d.y), iz = frcp(r.d.z);  // 1.0f / direction, aabb.cuh:48
-  const bool nx = ix < 0.0f, ny = iy < 0.0f, nz = iz < 0.0f;
+  // float4 index of the NEAR plane vector of each axis inside a node (lox 0, loy 1, loz 2, hix 3, hiy 4, hiz 5)
+  const int onx = ix < 0.0f ? 3 : 0, ony = iy < 0.0f ? 4 : 1, onz = iz < 0.0f ? 5 : 2;
   uint32_t stack[RT_STACK];  // interior nodes only
   uint32_t lq_ref[RT_LEAFQ], lq_tlp[RT_LEAFQ];
   float lq_tn[RT_LEAFQ];
@@ -265,41 +291,46 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
       if (can) {
         RT_COUNT(0, 1);
         const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
-        const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
-        const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+        // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0. The swap is
+        // done by the LOAD: per-ray offsets pick the near / far plane vectors of the node, no per-child selects.
+        const float4 nxp = __ldg(np + onx), fxp = __ldg(np + (3 - onx));
+        const float4 nyp = __ldg(np + ony), fyp = __ldg(np + (5 - ony));
+        const float4 nzp = __ldg(np + onz), fzp = __ldg(np + (7 - onz));
         const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
         const uint4 tl = __ldg(reinterpret_cast<const uint4*>(np + 7));
-        const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w}, lz[4] = {loz.x, loz.y, loz.z, loz.w};
-        const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
-        float tn[4]; uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w}, ct[4] = {tl.x, tl.y, tl.z, tl.w};
+        const float ax[4] = {nxp.x, nxp.y, nxp.z, nxp.w}, bx[4] = {fxp.x, fxp.y, fxp.z, fxp.w};
+        const float ay[4] = {nyp.x, nyp.y, nyp.z, nyp.w}, by[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
+        const float az[4] = {nzp.x, nzp.y, nzp.z, nzp.w}, bz[4] = {fzp.x, fzp.y, fzp.z, fzp.w};
+        const uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w}, ct[4] = {tl.x, tl.y, tl.z, tl.w};
+        uint32_t key[4];  // interior children that are entered: (entry distance bits, child slot); else 0xFFFFFFFF
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0;
           // tmin = t0 > tmin ? t0 : tmin (== fmaxf, NaN keeps tmin); reject when tmax <= tmin.
-          float t0 = fmul(fsub(nx ? hx[c] : lx[c], r.o.x), ix), t1 = fmul(fsub(nx ? lx[c] : hx[c], r.o.x), ix);
-          float lo = fmaxf(t0, tmin), hi = fminf(t1, best.t);
-          t0 = fmul(fsub(ny ? hy[c] : ly[c], r.o.y), iy); t1 = fmul(fsub(ny ? ly[c] : hy[c], r.o.y), iy);
-          lo = fmaxf(t0, lo); hi = fminf(t1, hi);
-          t0 = fmul(fsub(nz ? hz[c] : lz[c], r.o.z), iz); t1 = fmul(fsub(nz ? lz[c] : hz[c], r.o.z), iz);
-          lo = fmaxf(t0, lo); hi = fminf(t1, hi);
-          tn[c] = (hi > lo && cr[c] != RT_NODE_EMPTY) ? lo : FLT_MAX;  // FLT_MAX = not entered (a real entry is < best.t <= FLT_MAX)
-          if (!(hi > lo)) cr[c] = RT_NODE_EMPTY;
+          float lo = fmaxf(fmul(fsub(ax[c], r.o.x), ix), tmin), hi = fminf(fmul(fsub(bx[c], r.o.x), ix), best.t);
+          lo = fmaxf(fmul(fsub(ay[c], r.o.y), iy), lo); hi = fminf(fmul(fsub(by[c], r.o.y), iy), hi);
+          lo = fmaxf(fmul(fsub(az[c], r.o.z), iz), lo); hi = fminf(fmul(fsub(bz[c], r.o.z), iz), hi);
+          const bool entered = hi > lo && cr[c] != RT_NODE_EMPTY;
+          const bool interior = (cr[c] & RT_NODE_FLAG) != 0;
+          // lo >= tmin > 0, so its bit pattern orders like the float; the low two mantissa bits carry the child slot
+          key[c] = (entered && interior) ? ((__float_as_uint(lo) & ~3u) | (uint32_t)c) : 0xFFFFFFFFu;
+          if (entered && !interior) { lq_ref[nl] = cr[c]; lq_tlp[nl] = ct[c]; lq_tn[nl] = lo; ++nl; }  // leaves need no order
         }
-        RT_CSWAP(0, 1); RT_CSWAP(2, 3); RT_CSWAP(0, 2); RT_CSWAP(1, 3); RT_CSWAP(1, 2);  // nearest first
-        // leaves -> pending queue; interior children: nearest is next, the others are stacked far-to-near
-        uint32_t next = RT_NODE_EMPTY;
+        // interior children: nearest is the next node, the others are stacked far-to-near (5-comparator network on keys)
+#define RT_KSWAP(a, b) do { const uint32_t lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; } while (0)
+        RT_KSWAP(0, 1); RT_KSWAP(2, 3); RT_KSWAP(0, 2); RT_KSWAP(1, 3); RT_KSWAP(1, 2);
+#undef RT_KSWAP
 #pragma unroll
-        for (int k = 3; k >= 0; --k) {
-          const uint32_t c = cr[k];
-          if (c != RT_NODE_EMPTY && (c & RT_NODE_FLAG)) {
-            if (next != RT_NODE_EMPTY) { if (sp < RT_STACK) stack[sp++] = next; else atomicOr(overflow, 1u); }
-            next = c & 0x7FFFFFFFu;
+        for (int k = 3; k >= 1; --k) {
+          if (key[k] != 0xFFFFFFFFu) {
+            const uint32_t i = key[k] & 3u;
+            const uint32_t c = (i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0]);
+            if (sp < RT_STACK) stack[sp++] = c & 0x7FFFFFFFu; else atomicOr(overflow, 1u);
           }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t c = cr[k];
-          if (c != RT_NODE_EMPTY && !(c & RT_NODE_FLAG)) { lq_ref[nl] = c; lq_tlp[nl] = ct[k]; lq_tn[nl] = tn[k]; ++nl; }
+        uint32_t next = RT_NODE_EMPTY;
+        if (key[0] != 0xFFFFFFFFu) {
+          const uint32_t i = key[0] & 3u;
+          next = ((i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0])) & 0x7FFFFFFFu;
         }
         if (next != RT_NODE_EMPTY) cur = next;
         else if (sp > 0) cur = stack[--sp];

@@ -26,12 +26,12 @@ struct alignas(16) DSphere {  // sphere.cuh:95-100
   float dx, dy, dz;           // center.B (= c1 - c0; 0 for a static sphere)
   int mat;
 };
-struct alignas(16) DQuad {    // quad.cuh:14-21
-  float Qx, Qy, Qz, D;
-  float ux, uy, uz; int mat;
-  float vx, vy, vz, pad0;
-  float wx, wy, wz, pad1;
-  float nx, ny, nz, pad2;
+struct alignas(16) DQuad {    // quad.cuh:14-21; plane (normal, D) first: a box test reads the six planes before anything else
+  float nx, ny, nz, D;
+  float Qx, Qy, Qz; int mat;
+  float ux, uy, uz, pad0;
+  float vx, vy, vz, pad1;
+  float wx, wy, wz, pad2;
 };
 enum XformKind : int { X_TRANSLATE = 0, X_ROTATE_Y = 1 };
 struct alignas(16) DXform {   // hittable.cuh:40-149
