@@ -59,6 +59,7 @@ template <class T> struct DBuf {
   ~DBuf() { free(); }
 };
 
+#define RT_MAX_POOLS 4
 struct rt_scene {
   int device = 0;
   SceneDesc sd;
@@ -70,11 +71,12 @@ struct rt_scene {
   DScene dscene;
   int n_nodes = 0; float bvh_ms = 0.f; uint64_t h2d_bytes = 0;
   // render state
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, pool_stream[RT_MAX_POOLS] = {nullptr};  // pool 0 runs on `stream`
   DBuf<float4> ray_o, ray_d, thr, rad, col; DBuf<float2> hit; DBuf<uint32_t> rng;
   DBuf<int> queues, order;
-  DBuf<WaveCounters> counters;
-  WaveCounters* h_counters = nullptr;  // pinned
+  DBuf<WaveCounters> counters;          // one per slot pool
+  DBuf<unsigned long long> next_work;
+  WaveCounters* h_counters = nullptr;  // pinned, one per slot pool
   DBuf<float> accum, fb, aov_t; DBuf<int> aov_obj, aov_mat; DBuf<unsigned long long> acc64;
   size_t slots_cap = 0, pix_cap = 0, accum_valid_pix = 0;
   RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
@@ -82,6 +84,7 @@ struct rt_scene {
     for (auto p : image_px) cudaFree(p);
     if (h_counters) cudaFreeHost(h_counters);
     if (stream) cudaStreamDestroy(stream);
+    for (int k = 1; k < RT_MAX_POOLS; ++k) if (pool_stream[k]) cudaStreamDestroy(pool_stream[k]);
   }
 };
 
@@ -300,7 +303,10 @@ extern "C" int rt_build_scene(const rt_scene_desc* desc, rt_scene** out) {
   s->rank = reference_leaf_order(s->sd);
   if (upload_scene(s)) { delete s; return 1; }
   if (cudaStreamCreate(&s->stream) != cudaSuccess) { delete s; return fail("cudaStreamCreate failed"); }
-  if (cudaMallocHost(&s->h_counters, sizeof(WaveCounters)) != cudaSuccess) { delete s; return fail("cudaMallocHost failed"); }
+  s->pool_stream[0] = s->stream;
+  for (int k = 1; k < RT_MAX_POOLS; ++k)
+    if (cudaStreamCreate(&s->pool_stream[k]) != cudaSuccess) { delete s; return fail("cudaStreamCreate failed"); }
+  if (cudaMallocHost(&s->h_counters, RT_MAX_POOLS * sizeof(WaveCounters)) != cudaSuccess) { delete s; return fail("cudaMallocHost failed"); }
   *out = s;
   return 0;
 }
@@ -351,7 +357,7 @@ extern "C" int rt_scene_export_host(const rt_scene_desc* desc, void* buf, size_t
 static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rng, bool aov) {
   if (n_slots > s->slots_cap) {
     CU(s->ray_o.alloc(n_slots)); CU(s->ray_d.alloc(n_slots)); CU(s->thr.alloc(n_slots)); CU(s->rad.alloc(n_slots));
-    CU(s->col.alloc(n_slots)); CU(s->hit.alloc(n_slots)); CU(s->order.alloc(n_slots + 32 * (Q_COUNT + 1)));
+    CU(s->col.alloc(n_slots)); CU(s->hit.alloc(n_slots)); CU(s->order.alloc(n_slots + RT_MAX_POOLS * 32 * (Q_COUNT + 1)));
     CU(s->queues.alloc(n_slots * Q_COUNT));
     s->rng.free();
     s->slots_cap = n_slots;
@@ -363,7 +369,7 @@ static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rn
     s->pix_cap = n_pix; s->accum_valid_pix = 0;
   }
   if (aov && s->aov_obj.n < n_pix) { CU(s->aov_obj.alloc(s->pix_cap)); CU(s->aov_mat.alloc(s->pix_cap)); CU(s->aov_t.alloc(s->pix_cap)); }
-  if (!s->counters.p) CU(s->counters.alloc(1));
+  if (!s->counters.p) { CU(s->counters.alloc(RT_MAX_POOLS)); CU(s->next_work.alloc(1)); }
   return 0;
 }
 
@@ -392,7 +398,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   if (ref_rng) {
     P.n_slots = (int)n_pix;  // a slot is a pixel: one sequential XORWOW stream each
   } else {
-    long long target = p->slots > 0 ? p->slots : 1024 * 1024;
+    long long target = p->slots > 0 ? p->slots : 2 * 1024 * 1024;  // sweep on C4: 1 Mi .. 4 Mi within 2%, 512 Ki -8%
     if (p->slots <= 0) if (const char* e = getenv("RT_SLOTS")) target = atoll(e);
     target = (target + 127) / 128 * 128;
     P.n_slots = (int)std::max<long long>(0, std::min<long long>(target, P.work_total));
@@ -405,70 +411,122 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   const float gamma = p->gamma > 0 ? p->gamma : 2.2f;
   if (ensure_buffers(s, std::max(P.n_slots, 1), n_pix, ref_rng, p->aov != 0)) return 1;
 
+  // Slot pools: the slots are split into independent halves, each running its own trace -> shade chain on its own
+  // stream. k_trace is issue-bound and k_shade latency-bound, so letting one pool's shade run under the other
+  // pool's trace fills issue slots that a single chain leaves idle. The pools share only the work counter and the
+  // fixed-point accumulators (atomics). Reference-RNG mode and per-kernel profiling use one pool.
+  int n_pools = (ref_rng || p->profile) ? 1 : P.n_slots >= 1024 * 1024 ? 4 : P.n_slots >= 256 * 1024 ? 2 : 1;  // C4: 1 pool 2480, 2 pools 2810, 4 pools 2870 Mrays/s
+  if (const char* e = getenv("RT_POOLS")) n_pools = (!ref_rng && P.n_slots >= RT_MAX_POOLS * RT_BLOCK) ? std::max(1, std::min(RT_MAX_POOLS, atoi(e))) : 1;
   PathArrays A;
   A.ray_o = s->ray_o.p; A.ray_d = s->ray_d.p; A.hit = s->hit.p; A.thr = s->thr.p; A.rad = s->rad.p; A.col = s->col.p;
-  A.rng = s->rng.p; A.acc64 = s->acc64.p; A.order = s->order.p;
+  A.rng = s->rng.p; A.acc64 = s->acc64.p; A.order = s->order.p; A.next_work = s->next_work.p;
   cudaStream_t st = s->stream;
-  cudaEvent_t e0, e1, ev;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaStream_t* streams = s->pool_stream;
+  cudaEvent_t e0, e1, evs[RT_MAX_POOLS];
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  for (int k = 0; k < RT_MAX_POOLS; ++k) CU(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
   CU(cudaEventRecord(e0, st));
+  // pool geometry: pool k owns a contiguous range of the slots and the same ranges of the queues / order arrays
+  RenderParams Pp[RT_MAX_POOLS];
+  PathArrays Ap[RT_MAX_POOLS];
+  int* queues_p[RT_MAX_POOLS];
   {
-    WaveCounters init; memset(&init, 0, sizeof(init));
-    init.order_len = P.n_slots;
-    *s->h_counters = init;
-    CU(cudaMemcpyAsync(s->counters.p, s->h_counters, sizeof(WaveCounters), cudaMemcpyHostToDevice, st));
+    const int per = (P.n_slots / n_pools + RT_BLOCK - 1) / RT_BLOCK * RT_BLOCK;
+    int base = 0;
+    for (int k = 0; k < n_pools; ++k) {
+      const int n = (k == n_pools - 1) ? P.n_slots - base : std::min(per, P.n_slots - base);
+      Pp[k] = P; Pp[k].n_slots = n;
+      Ap[k] = A;
+      Ap[k].ray_o += base; Ap[k].ray_d += base; Ap[k].hit += base; Ap[k].thr += base; Ap[k].rad += base; Ap[k].col += base;
+      Ap[k].order += base + k * 32 * (Q_COUNT + 1);
+      queues_p[k] = s->queues.p + (size_t)Q_COUNT * base;
+      base += n;
+    }
+  }
+  {
+    for (int k = 0; k < RT_MAX_POOLS; ++k) { memset(&s->h_counters[k], 0, sizeof(WaveCounters)); if (k < n_pools) s->h_counters[k].order_len = Pp[k].n_slots; }
+    CU(cudaMemcpyAsync(s->counters.p, s->h_counters, RT_MAX_POOLS * sizeof(WaveCounters), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(s->next_work.p, 0, sizeof(unsigned long long), st));
     if (!ref_rng && n_pix > 0) CU(cudaMemsetAsync(s->acc64.p, 0, 3 * n_pix * sizeof(unsigned long long), st));
   }
   const int B = RT_BLOCK;
   int launches = 0, waves = 0, prof_waves = 0;
   double prof_trace_ms = 0.0, prof_shade_ms = 0.0;
   if (P.n_slots > 0 && P.sample_count > 0) {
-    const int G = (P.n_slots + B - 1) / B;
-    if (ref_rng) k_init<RNG_REFERENCE><<<G, B, 0, st>>>(P, A);
-    else k_init<RNG_PHILOX><<<G, B, 0, st>>>(P, A);
-    ++launches;
-    // Every wave runs k_trace over ALL slots (a slot whose sample ended regenerates there) and k_shade over the
-    // queues that wave filled. The host reads the queue fills back every `batch` waves: a wave that traced no
-    // ray means every slot is dead, i.e. the job is done.
+    // Every wave of a pool runs k_trace over its slots (a slot whose sample ended regenerates there) and k_shade over
+    // the queues that wave filled. The host reads the queue fills back every `batch` waves: a wave that traced no
+    // ray means every slot of the pool is dead; the job is done when both pools are.
     int batch = 8;
     if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
     FILE* wlog = nullptr;  // diagnostics: one line per wave (rays of the wave, k_trace ms, k_shade ms)
     if (p->profile) if (const char* e = getenv("RT_WAVE_LOG")) { wlog = fopen(e, "a"); batch = 1; }
-    int parity = 0;
     std::vector<cudaEvent_t> pev;
     if (p->profile) { pev.resize(3 * batch); for (auto& e : pev) CU(cudaEventCreate(&e)); }
-    const int Gs = (P.n_slots + 32 * Q_COUNT + B - 1) / B;
-    bool done = false;
-    while (!done) {
+    cudaEvent_t eset;
+    CU(cudaEventCreateWithFlags(&eset, cudaEventDisableTiming));
+    CU(cudaEventRecord(eset, st));
+    for (int k = 1; k < n_pools; ++k) CU(cudaStreamWaitEvent(streams[k], eset, 0));  // the other pools start after the counters are set
+    cudaEventDestroy(eset);
+    int G[RT_MAX_POOLS], Gs[RT_MAX_POOLS];
+    for (int k = 0; k < n_pools; ++k) {
+      G[k] = (Pp[k].n_slots + B - 1) / B;
+      Gs[k] = (Pp[k].n_slots + 32 * Q_COUNT + B - 1) / B;
+      if (ref_rng) k_init<RNG_REFERENCE><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
+      else k_init<RNG_PHILOX><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
+      ++launches;
+    }
+    int parity = 0;
+    bool done[RT_MAX_POOLS];
+    for (int k = 0; k < RT_MAX_POOLS; ++k) done[k] = k >= n_pools;
+    auto all_done = [&]() { bool d = true; for (int k = 0; k < n_pools; ++k) d = d && done[k]; return d; };
+    while (!all_done()) {
       for (int w = 0; w < batch; ++w) {
-        if (p->profile) CU(cudaEventRecord(pev[3 * w], st));
-        if (ref_rng) k_trace<RNG_REFERENCE><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
-        else k_trace<RNG_PHILOX><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
-        if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], st));
-        if (ref_rng) k_shade<RNG_REFERENCE><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
-        else k_shade<RNG_PHILOX><<<Gs, B, 0, st>>>(s->dscene, P, A, s->queues.p, s->counters.p, parity);
-        if (p->profile) CU(cudaEventRecord(pev[3 * w + 2], st));
-        parity ^= 1; launches += 2; ++waves;
+        for (int k = 0; k < n_pools; ++k) {
+          if (done[k]) continue;
+          cudaStream_t sk = streams[k];
+          WaveCounters* Ck = s->counters.p + k;
+          if (p->profile) CU(cudaEventRecord(pev[3 * w], sk));
+          if (ref_rng) k_trace<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          else k_trace<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], sk));
+          if (ref_rng) k_shade<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          else k_shade<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          if (p->profile) CU(cudaEventRecord(pev[3 * w + 2], sk));
+          launches += 2;
+        }
+        parity ^= 1; ++waves;
       }
       // queue fills of the LAST wave of the batch (k_shade zeroes the other parity for the next k_trace)
-      CU(cudaMemcpyAsync(s->h_counters, s->counters.p, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-      CU(cudaEventRecord(ev, st));
-      CU(cudaEventSynchronize(ev));
-      int last = 0;
-      for (int k = 0; k < Q_COUNT; ++k) last += s->h_counters->n_queue[parity ^ 1][k];
-      done = last == 0;
+      for (int k = 0; k < n_pools; ++k) {
+        if (done[k]) continue;
+        CU(cudaMemcpyAsync(&s->h_counters[k], s->counters.p + k, sizeof(WaveCounters), cudaMemcpyDeviceToHost, streams[k]));
+        CU(cudaEventRecord(evs[k], streams[k]));
+      }
+      int last_all = 0;
+      for (int k = 0; k < n_pools; ++k) {
+        if (done[k]) continue;
+        CU(cudaEventSynchronize(evs[k]));
+        int last = 0;
+        for (int q = 0; q < Q_COUNT; ++q) last += s->h_counters[k].n_queue[parity ^ 1][q];
+        done[k] = last == 0;
+        last_all += last;
+      }
       if (p->profile) {
         for (int w = 0; w < batch; ++w) {
           float a = 0.f, b = 0.f;
           CU(cudaEventElapsedTime(&a, pev[3 * w], pev[3 * w + 1]));
           CU(cudaEventElapsedTime(&b, pev[3 * w + 1], pev[3 * w + 2]));
           prof_trace_ms += a; prof_shade_ms += b; ++prof_waves;
-          if (wlog) fprintf(wlog, "%d %d %.4f %.4f\n", prof_waves, last, a, b);
+          if (wlog) fprintf(wlog, "%d %d %.4f %.4f\n", prof_waves, last_all, a, b);
         }
       }
     }
     for (auto& e : pev) cudaEventDestroy(e);
     if (wlog) fclose(wlog);
+    for (int k = 1; k < n_pools; ++k) {  // pool 0's stream carries on alone: it waits for the other pools' last kernels
+      CU(cudaEventRecord(evs[k], streams[k]));
+      CU(cudaStreamWaitEvent(st, evs[k], 0));
+    }
   }
   {
     const int Gp = (int)((n_pix + 255) / 256);
@@ -485,18 +543,21 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   if (p->aov && n_pix > 0) {
     k_aov<<<(int)((n_pix + B - 1) / B), B, 0, st>>>(s->dscene, P, s->aov_obj.p, s->aov_mat.p, s->aov_t.p, s->counters.p);
   }
-  CU(cudaMemcpyAsync(s->h_counters, s->counters.p, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s->h_counters, s->counters.p, RT_MAX_POOLS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ev);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (int k = 0; k < RT_MAX_POOLS; ++k) cudaEventDestroy(evs[k]);
+  unsigned long long rays_all = 0; unsigned int overflow_all = 0, nonfinite_all = 0;
+  for (int k = 0; k < RT_MAX_POOLS; ++k) { rays_all += s->h_counters[k].rays; overflow_all |= s->h_counters[k].overflow; nonfinite_all += s->h_counters[k].nonfinite; }
   s->last = P; s->has_aov = p->aov != 0; s->last_gamma = gamma; s->last_spp_total = spp_total;
   rt_render_stats& R = s->stats;
   memset(&R, 0, sizeof(R));
-  R.device_ms = ms; R.rays = s->h_counters->rays; R.samples = (uint64_t)n_pix * (uint64_t)P.sample_count;
+  R.device_ms = ms; R.rays = rays_all; R.samples = (uint64_t)n_pix * (uint64_t)P.sample_count;
   R.waves = waves; R.kernel_launches = launches; R.rows_local = P.rows_local; R.nx = P.nx;
-  R.nonfinite_samples = s->h_counters->nonfinite; R.n_slots = P.n_slots; R.stack_overflow = s->h_counters->overflow;
+  R.nonfinite_samples = (int32_t)nonfinite_all; R.n_slots = P.n_slots; R.stack_overflow = overflow_all;
   R.profiled_waves = prof_waves; R.trace_ms = prof_trace_ms; R.shade_ms = prof_shade_ms;
   if (device_ms) *device_ms = ms;
   if (rays) *rays = R.rays;

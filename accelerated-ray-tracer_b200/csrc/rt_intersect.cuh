@@ -249,9 +249,11 @@ RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
 // (First version: leaf tests inline in the node loop ran at 2-6 active lanes per instruction on the
 // Book-2 final scene, profiles/r01.)
 #define RT_STACK 48
+#ifndef RT_LEAFQ
 #define RT_LEAFQ 8         // pending leaves per lane
+#endif
 #ifndef RT_NODE_MIN
-#define RT_NODE_MIN 12     // leaf phase starts when fewer lanes than this can still expand a node
+#define RT_NODE_MIN 3      // leaf phase starts when fewer lanes than this can still expand a node (A/B on C4: 3 beats 1, 8, 12, 16)
 #endif
 struct Hit { float t; int tlp; int face; };
 #ifdef RT_STATS  // diagnostics build only (tools/): per-ray work counters

@@ -37,6 +37,7 @@ struct PathArrays {
   uint32_t* rng;   // reference-RNG mode: 6 words per slot, SoA [6][n_slots]
   unsigned long long* acc64;  // Philox mode: per local pixel 3 x fixed-point (2^-32) radiance sums
   int* order;      // k_trace thread -> slot: the previous wave's shade-queue layout (-1 = hole), see k_shade
+  unsigned long long* next_work;  // Philox mode: next work item to hand out (shared by all slot pools)
 };
 
 struct WaveCounters {
@@ -46,7 +47,6 @@ struct WaveCounters {
   unsigned long long samples;  // finished samples
   unsigned int overflow;       // traversal stack overflow flag (must stay 0)
   unsigned int nonfinite;      // Philox mode: samples dropped because their radiance was inf/NaN
-  unsigned long long next_work; // Philox mode: next work item to hand out
 };
 
 struct RenderParams {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RenderParams P, Pa
   // ---- path regeneration (main.cu:119-123): a slot whose sample has ended takes the next one ----
   const bool need = state == SLOT_NEEDS_SAMPLE;
   if constexpr (MODE == RNG_PHILOX) {
-    const unsigned long long w = block_reserve(&C->next_work, need, s_cnt, &s_wbase);
+    const unsigned long long w = block_reserve(A.next_work, need, s_cnt, &s_wbase);
     if (need) {
       if (w < (unsigned long long)P.work_total) {
         int lpix, sample;
