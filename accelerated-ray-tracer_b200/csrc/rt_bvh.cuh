@@ -1,11 +1,17 @@
 // rt_bvh.cuh — device-side construction of the 4-wide BVH over the top-level objects.
 //
 // Replaces bvh_node's constructor (bvh.cuh:29-84): one GPU thread, recursive `new`, O(n^2) selection
-// sort per level. Here: 63-bit Morton codes of the box centroids, radix sort (CUB), Karras' parallel
-// radix tree (HPG 2012), bottom-up box fit with atomic arrival flags, then a greedy surface-area
-// collapse of the binary tree into 4-wide nodes. The topology differs from the reference's on
-// purpose; what must match is which objects a ray can hit (leaf boxes are the objects' own boxes,
-// interior boxes exact unions) — see closest_hit in rt_intersect.cuh.
+// sort per level. Here: 63-bit Morton codes of the box centroids, radix sort (CUB), then PLOC
+// (parallel locally-ordered clustering, Meister & Bittner 2018): every cluster looks RT_PLOC_RADIUS
+// places left and right along the Morton order for the partner with the smallest merged surface
+// area, mutual nearest neighbours merge, the array is compacted, repeat until one cluster is left.
+// Unlike a plain radix tree over the codes this keeps oversized objects (the r = 5000 fog sphere of
+// the Book-2 final scene, Cornell walls) out of the deep levels: nothing wants to merge with them until
+// the end, so they end up next to the root instead of inflating every ancestor box on some deep path.
+// Finally a greedy surface-area collapse of the binary tree into 4-wide nodes. The topology differs
+// from the reference's on purpose; what must match is which objects a ray can hit (leaf boxes are the
+// objects' own boxes, interior boxes exact unions) — see closest_hit in rt_intersect.cuh.
+// (The Karras radix-tree kernels below are kept as the RT_BVH_LBVH build variant for A/B runs.)
 #pragma once
 #include <cub/cub.cuh>
 #include "rt_scene_dev.h"
@@ -120,13 +126,78 @@ RT_D float box_area(const BuildBox& b) {
   return dx * dy + dy * dz + dz * dx;
 }
 
+// ---- PLOC ----
+#ifndef RT_PLOC_RADIUS
+#define RT_PLOC_RADIUS 16
+#endif
+#define RT_PLOC_BLOCK 256
+// Binary tree ids: interior nodes 0..n-2 (in creation order), leaves n-1..2n-2 (leaf k = sorted object k).
+__global__ void k_ploc_init(const BuildBox* boxes, const int* sorted, int n, int* cl, BuildBox* nbox) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  cl[k] = n - 1 + k;
+  nbox[n - 1 + k] = boxes[sorted[k]];
+}
+// nn[i] = the cluster within RT_PLOC_RADIUS places of i whose union with i has the smallest surface area.
+// Ties are broken by a total order on PAIRS (even left position first, then the smaller left position), which
+// (a) guarantees a mutual pair every round and (b) pairs a run of equidistant clusters as (0,1)(2,3)(4,5)...
+// instead of merging one pair per round into a chain: regular grids (the C5 sphere grid) are full of such runs.
+__global__ void __launch_bounds__(RT_PLOC_BLOCK) k_ploc_nn(const int* cl, int m, const BuildBox* nbox, int* nn) {
+  __shared__ BuildBox sb[RT_PLOC_BLOCK + 2 * RT_PLOC_RADIUS];
+  const int start = blockIdx.x * RT_PLOC_BLOCK - RT_PLOC_RADIUS;
+  for (int t = threadIdx.x; t < RT_PLOC_BLOCK + 2 * RT_PLOC_RADIUS; t += RT_PLOC_BLOCK) {
+    const int g = start + t;
+    if (g >= 0 && g < m) sb[t] = nbox[cl[g]];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * RT_PLOC_BLOCK + threadIdx.x;
+  if (i >= m) return;
+  const BuildBox a = sb[threadIdx.x + RT_PLOC_RADIUS];
+  float best = FLT_MAX; int bj = -1; unsigned bkey = 0xFFFFFFFFu;
+  for (int d = -RT_PLOC_RADIUS; d <= RT_PLOC_RADIUS; ++d) {
+    const int j = i + d;
+    if (d == 0 || j < 0 || j >= m) continue;
+    const BuildBox b = sb[threadIdx.x + RT_PLOC_RADIUS + d];
+    BuildBox u;
+    for (int x = 0; x < 3; ++x) { u.mn[x] = fminf(a.mn[x], b.mn[x]); u.mx[x] = fmaxf(a.mx[x], b.mx[x]); }
+    const float ar = box_area(u);
+    const unsigned lft = (unsigned)min(i, j);
+    const unsigned key = ((lft & 1u) << 31) | lft;  // the right partner is then fixed by the distance |d|: ascending |d| below
+    if (ar < best || (ar == best && (key < bkey || (key == bkey && abs(d) < abs(bj - i))))) { best = ar; bj = j; bkey = key; }
+  }
+  nn[i] = bj;
+}
+// Mutual nearest neighbours merge into a new interior node that takes the place of the LEFT partner.
+__global__ void k_ploc_merge(const int* cl, int m, const int* nn, BuildBox* nbox, int* left, int* right, int* next_id, int* cl_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int j = nn[i];
+  int out = cl[i];
+  if (j >= 0 && nn[j] == i) {
+    if (i < j) {
+      const int id = atomicAdd(next_id, 1);
+      const int l = cl[i], r = cl[j];
+      left[id] = l; right[id] = r;
+      const BuildBox a = nbox[l], b = nbox[r];
+      BuildBox u;
+      for (int x = 0; x < 3; ++x) { u.mn[x] = fminf(a.mn[x], b.mn[x]); u.mx[x] = fmaxf(a.mx[x], b.mx[x]); }
+      nbox[id] = u;
+      out = id;
+    } else {
+      out = -1;  // absorbed by its partner
+    }
+  }
+  cl_out[i] = out;
+}
+struct PlocAlive { __device__ bool operator()(int v) const { return v >= 0; } };
+
 // Collapse to 4-wide nodes. One CTA, level-synchronous work queue: task = (binary node, output node).
 // Each task opens the interior child with the largest surface area until it has 4 children.
-__global__ void __launch_bounds__(1024) k_bvh_collapse(int n, const int* left, const int* right, const BuildBox* nbox,
+__global__ void __launch_bounds__(1024) k_bvh_collapse(int n, int root, const int* left, const int* right, const BuildBox* nbox,
                                                        const int* sorted, const uint32_t* tlp_ref, BVH4Node* out,
                                                        int* n_out, int2* qa, int2* qb) {
   __shared__ int s_count, s_next;
-  if (threadIdx.x == 0) { qa[0] = make_int2(0, 0); s_count = 1; s_next = 0; *n_out = 1; }
+  if (threadIdx.x == 0) { qa[0] = make_int2(root, 0); s_count = 1; s_next = 0; *n_out = 1; }
   __syncthreads();
   int2* cur = qa; int2* nxt = qb;
   while (true) {
@@ -146,6 +217,10 @@ __global__ void __launch_bounds__(1024) k_bvh_collapse(int n, const int* left, c
         kids[nk++] = right[open];
       }
       BVH4Node node;
+      int n_int = 0;  // interior children get consecutive output nodes (and queue entries): siblings share cache lines
+      for (int c = 0; c < nk; ++c) n_int += kids[c] < n - 1;
+      int o_next = n_int ? atomicAdd(n_out, n_int) : 0;
+      int q_next = n_int ? atomicAdd(&s_next, n_int) : 0;
       for (int c = 0; c < 4; ++c) {
         if (c < nk) {
           const BuildBox b = nbox[kids[c]];
@@ -155,10 +230,9 @@ __global__ void __launch_bounds__(1024) k_bvh_collapse(int n, const int* left, c
             const int obj = sorted[kids[c] - (n - 1)];
             node.child[c] = tlp_ref[obj]; node.tlp[c] = (uint32_t)obj;
           } else {
-            const int o = atomicAdd(n_out, 1);
+            const int o = o_next++;
             node.child[c] = RT_NODE_FLAG | (uint32_t)o; node.tlp[c] = 0;
-            const int q = atomicAdd(&s_next, 1);
-            nxt[q] = make_int2(kids[c], o);
+            nxt[q_next++] = make_int2(kids[c], o);
           }
         } else {
           node.lox[c] = node.loy[c] = node.loz[c] = FLT_MAX;

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "rt_api.h"
@@ -31,7 +32,16 @@ struct CudaDevMath : DevMath {
   float* d = nullptr; bool ok = true;
   CudaDevMath() { if (cudaMalloc(&d, sizeof(float)) != cudaSuccess) ok = false; }
   ~CudaDevMath() { if (d) cudaFree(d); }
+  std::map<std::pair<int, uint32_t>, float> memo;  // generators ask for the same few angles over and over
   float call(int op, float x) {
+    uint32_t bits; memcpy(&bits, &x, 4);
+    auto it = memo.find(std::make_pair(op, bits));
+    if (it != memo.end()) return it->second;
+    const float v = eval(op, x);
+    memo[std::make_pair(op, bits)] = v;
+    return v;
+  }
+  float eval(int op, float x) {
     float h = 0.f;
     k_devmath<<<1, 1>>>(op, x, d);
     if (cudaMemcpy(&h, d, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
@@ -246,13 +256,38 @@ static int upload_scene(rt_scene* s) {
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, n, 0, 63);
     DBuf<unsigned char> tmp; CU(tmp.alloc(tmp_bytes));
     cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, n, 0, 63);
-    DBuf<int> left, right, parent, flags; DBuf<BuildBox> nbox; DBuf<int2> qa, qb;
-    CU(left.alloc(n)); CU(right.alloc(n)); CU(parent.alloc(2 * n)); CU(flags.alloc(n)); CU(nbox.alloc(2 * n));
-    CU(qa.alloc(n)); CU(qb.alloc(n));
+    DBuf<int> left, right; DBuf<BuildBox> nbox; DBuf<int2> qa, qb;
+    CU(left.alloc(n)); CU(right.alloc(n)); CU(nbox.alloc(2 * n)); CU(qa.alloc(n)); CU(qb.alloc(n));
+    int root = 0;
+#ifdef RT_BVH_LBVH
+    DBuf<int> parent, flags;
+    CU(parent.alloc(2 * n)); CU(flags.alloc(n));
     CU(cudaMemset(flags.p, 0, n * sizeof(int)));
     k_bvh_karras<<<G, B>>>(k_out.p, n, left.p, right.p, parent.p);
     k_bvh_fit<<<G, B>>>(d_boxes.p, v_out.p, n, left.p, right.p, parent.p, nbox.p, flags.p);
-    k_bvh_collapse<<<1, 1024>>>(n, left.p, right.p, nbox.p, v_out.p, d_refs.p, s->nodes.p, d_nout.p, qa.p, qb.p);
+#else
+    // PLOC rounds: nearest neighbour search -> merge -> compaction, until one cluster (the root) is left
+    DBuf<int> cl_a, cl_b, nn, next_id, d_m;
+    CU(cl_a.alloc(n)); CU(cl_b.alloc(n)); CU(nn.alloc(n)); CU(next_id.alloc(1)); CU(d_m.alloc(1));
+    CU(cudaMemset(next_id.p, 0, sizeof(int)));
+    size_t sel_bytes = 0;
+    cub::DeviceSelect::If(nullptr, sel_bytes, cl_b.p, cl_a.p, d_m.p, n, PlocAlive());
+    DBuf<unsigned char> sel_tmp; CU(sel_tmp.alloc(sel_bytes));
+    k_ploc_init<<<G, B>>>(d_boxes.p, v_out.p, n, cl_a.p, nbox.p);
+    int m = n, rounds = 0;
+    while (m > 1) {
+      const int Gm = (m + RT_PLOC_BLOCK - 1) / RT_PLOC_BLOCK;
+      k_ploc_nn<<<Gm, RT_PLOC_BLOCK>>>(cl_a.p, m, nbox.p, nn.p);
+      k_ploc_merge<<<Gm, RT_PLOC_BLOCK>>>(cl_a.p, m, nn.p, nbox.p, left.p, right.p, next_id.p, cl_b.p);
+      cub::DeviceSelect::If(sel_tmp.p, sel_bytes, cl_b.p, cl_a.p, d_m.p, m, PlocAlive());
+      int m_new = 0;
+      CU(cudaMemcpy(&m_new, d_m.p, sizeof(int), cudaMemcpyDeviceToHost));
+      if (m_new >= m || ++rounds > 4096) return fail("upload_scene: PLOC made no progress");
+      m = m_new;
+    }
+    CU(cudaMemcpy(&root, cl_a.p, sizeof(int), cudaMemcpyDeviceToHost));
+#endif
+    k_bvh_collapse<<<1, 1024>>>(n, root, left.p, right.p, nbox.p, v_out.p, d_refs.p, s->nodes.p, d_nout.p, qa.p, qb.p);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
   }
@@ -467,10 +502,11 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     CU(cudaEventRecord(eset, st));
     for (int k = 1; k < n_pools; ++k) CU(cudaStreamWaitEvent(streams[k], eset, 0));  // the other pools start after the counters are set
     cudaEventDestroy(eset);
-    int G[RT_MAX_POOLS], Gs[RT_MAX_POOLS];
+    int G[RT_MAX_POOLS], Gs[RT_MAX_POOLS], Gt[RT_MAX_POOLS];
     for (int k = 0; k < n_pools; ++k) {
       G[k] = (Pp[k].n_slots + B - 1) / B;
       Gs[k] = (Pp[k].n_slots + 32 * Q_COUNT + B - 1) / B;
+      Gt[k] = (Pp[k].n_slots + 32 * Q_COUNT + RT_TBLOCK - 1) / RT_TBLOCK;
       if (ref_rng) k_init<RNG_REFERENCE><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
       else k_init<RNG_PHILOX><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
       ++launches;
@@ -486,8 +522,8 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
           cudaStream_t sk = streams[k];
           WaveCounters* Ck = s->counters.p + k;
           if (p->profile) CU(cudaEventRecord(pev[3 * w], sk));
-          if (ref_rng) k_trace<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
-          else k_trace<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          if (ref_rng) k_trace<RNG_REFERENCE><<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          else k_trace<RNG_PHILOX><<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
           if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], sk));
           if (ref_rng) k_shade<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
           else k_shade<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);

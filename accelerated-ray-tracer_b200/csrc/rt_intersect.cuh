@@ -16,7 +16,10 @@ struct Ray { V3 o, d; float tm; };
 struct Rec { float t; V3 p, n; float u, v; int face; };  // face: which of a box's six quads was hit
 
 // ---- sphere (sphere.cuh:51-89) ----
-// T-only form used by traversal: returns the accepted root in (tmin, tmax) exclusive, like the reference.
+// T-only form: returns the accepted root in (tmin, tmax) exclusive, like the reference. TIE = true (traversal only)
+// also lets t == tmax through, so that leaf_accept can settle the exact tie by reference leaf order instead of by
+// whichever object this traversal happened to meet first.
+template <bool TIE = false>
 RT_D bool sphere_t(const DSphere& s, const Ray& r, float tmin, float tmax, float& t_out, V3& cc) {
   cc = vmad(r.tm, v3(s.dx, s.dy, s.dz), v3(s.cx, s.cy, s.cz));  // center.point_at_parameter(time)
   V3 oc = vsub(r.o, cc);
@@ -27,9 +30,9 @@ RT_D bool sphere_t(const DSphere& s, const Ray& r, float tmin, float tmax, float
   if (!(disc > 0.0f)) return false;
   float sq = fsqrt(disc);
   float t = fdiv(fsub(-b, sq), a);
-  if (t > tmin && t < tmax) { t_out = t; return true; }
+  if (t > tmin && (TIE ? t <= tmax : t < tmax)) { t_out = t; return true; }
   t = fdiv(fsub(sq, b), a);
-  if (t > tmin && t < tmax) { t_out = t; return true; }
+  if (t > tmin && (TIE ? t <= tmax : t < tmax)) { t_out = t; return true; }
   return false;
 }
 RT_D void sphere_uv(V3 n, float& u, float& v) {  // get_sphere_uv, sphere.cuh:42-49
@@ -116,7 +119,7 @@ RT_D bool box_hit(const DQuad* faces, const Ray& r, float tmin, float tmax, floa
 // ---- instance wrappers + leaves: generic hit of a non-medium geometry ref ----
 #define RT_MAX_XFORM 4
 // known_face >= 0 (shading): the box face k_trace found; only that quad is intersected again.
-template <bool FULL>
+template <bool FULL, bool TIE = false>
 RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax, bool want_uv, Rec& rec, int known_face = -1) {
   uint32_t chain[RT_MAX_XFORM];
   V3 dir_in[RT_MAX_XFORM];  // ray direction as each rotate_y saw it (for its normal flip)
@@ -142,7 +145,7 @@ RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax,
   if (ty == G_SPHERE) {
     const DSphere s = S.spheres[ix];
     float t; V3 cc;
-    if (!sphere_t(s, r, tmin, tmax, t, cc)) return false;
+    if (!sphere_t<TIE>(s, r, tmin, tmax, t, cc)) return false;
     rec.t = t;
     if (FULL) sphere_fill(s, r, t, cc, want_uv, rec);
   } else if (ty == G_QUAD) {
@@ -264,7 +267,11 @@ __device__ unsigned long long g_stats[8];  // 0 node expansions, 1 sphere tests,
 #endif
 
 RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int face, Hit& best) {
-  if (t < best.t || best.tlp < 0) { best.t = t; best.tlp = (int)tlp; best.face = face; return; }
+  if (t < best.t) { best.t = t; best.tlp = (int)tlp; best.face = face; return; }
+  if (best.tlp < 0) {  // t == the caller's t_max: only an inclusive test accepts that (quad.cuh:64 vs sphere.cuh:63)
+    if (ref_inclusive(S, ref)) { best.t = t; best.tlp = (int)tlp; best.face = face; }
+    return;
+  }
   // exact tie (t == best.t; only inclusive tests get here): order semantics of bvh_node::hit
   const int rn = S.tlp[tlp].rank, rb = S.tlp[best.tlp].rank;
   const bool take = (rn > rb) ? ref_inclusive(S, ref) : !ref_inclusive(S, S.tlp[best.tlp].ref);
@@ -348,7 +355,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
         if (k < nl && ref_type(lq_ref[k]) == G_SPHERE && lq_tn[k] < best.t) {
           float t; V3 cc;
           RT_COUNT(1, 1);
-          if (sphere_t(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
+          if (sphere_t<true>(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
         }
       }
       // quads, boxes, instances
@@ -360,7 +367,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
             if (ty != G_SPHERE && ty != G_MEDIUM && lq_tn[k] < best.t) {
               Rec rec; rec.face = 0;
               RT_COUNT(2, 1);
-              if (geom_hit<false>(S, lq_ref[k], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[k], lq_tlp[k], rec.t, rec.face, best);
+              if (geom_hit<false, true>(S, lq_ref[k], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[k], lq_tlp[k], rec.t, rec.face, best);
             }
           }
         }

@@ -127,8 +127,12 @@ RT_D Ray start_sample(const DScene& S, const RenderParams& P, const PathArrays& 
 #define RT_SHADE_MINB 3   // resident blocks per SM the shade kernel is compiled for (register cap 65536 / (256 * MINB))
 #endif
 #define RT_WARPS (RT_BLOCK / 32)
-template <class T>
-RT_D T block_reserve(T* counter, bool pred, int* s_cnt /*[RT_WARPS]*/, T* s_base) {
+#ifndef RT_TBLOCK
+#define RT_TBLOCK 256     // k_trace block size
+#endif
+#define RT_TWARPS (RT_TBLOCK / 32)
+template <int NW, class T>
+RT_D T block_reserve(T* counter, bool pred, int* s_cnt /*[NW]*/, T* s_base) {
   const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) s_cnt[warp] = __popc(m);
@@ -136,7 +140,7 @@ RT_D T block_reserve(T* counter, bool pred, int* s_cnt /*[RT_WARPS]*/, T* s_base
   if (threadIdx.x == 0) {
     int tot = 0;
 #pragma unroll
-    for (int w = 0; w < RT_WARPS; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+    for (int w = 0; w < NW; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
     *s_base = tot > 0 ? atomicAdd(counter, (T)tot) : (T)0;
   }
   __syncthreads();
@@ -182,11 +186,11 @@ __global__ void __launch_bounds__(RT_BLOCK) k_init(RenderParams P, PathArrays A)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RenderParams P, PathArrays A, int* __restrict__ queues,
-                                                    WaveCounters* C, int parity) {
-  __shared__ int s_cnt[RT_WARPS];
+__global__ void __launch_bounds__(RT_TBLOCK) k_trace(DScene S, RenderParams P, PathArrays A, int* __restrict__ queues,
+                                                     WaveCounters* C, int parity) {
+  __shared__ int s_cnt[RT_TWARPS];
   __shared__ unsigned long long s_wbase;
-  __shared__ int s_q[RT_WARPS][Q_COUNT];
+  __shared__ int s_q[RT_TWARPS][Q_COUNT];
   __shared__ int s_qbase[Q_COUNT];
   // Thread -> slot through the previous wave's queue layout: paths that hit the same material class sit next to
   // each other, and the primary rays regenerated behind the miss / light queues come out in pixel order, which
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RenderParams P, Pa
   // ---- path regeneration (main.cu:119-123): a slot whose sample has ended takes the next one ----
   const bool need = state == SLOT_NEEDS_SAMPLE;
   if constexpr (MODE == RNG_PHILOX) {
-    const unsigned long long w = block_reserve(A.next_work, need, s_cnt, &s_wbase);
+    const unsigned long long w = block_reserve<RT_TWARPS>(A.next_work, need, s_cnt, &s_wbase);
     if (need) {
       if (w < (unsigned long long)P.work_total) {
         int lpix, sample;
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace(DScene S, RenderParams P, Pa
   if (threadIdx.x < Q_COUNT) {
     int tot = 0;
 #pragma unroll
-    for (int w = 0; w < RT_WARPS; ++w) { const int c = s_q[w][threadIdx.x]; s_q[w][threadIdx.x] = tot; tot += c; }
+    for (int w = 0; w < RT_TWARPS; ++w) { const int c = s_q[w][threadIdx.x]; s_q[w][threadIdx.x] = tot; tot += c; }
     s_qbase[threadIdx.x] = tot > 0 ? atomicAdd(&C->n_queue[parity][threadIdx.x], tot) : 0;
   }
   __syncthreads();

@@ -1,0 +1,86 @@
+#!/usr/bin/env python3
+"""tools/summarize_profile.py <tag> — turn the raw ncu outputs in gpurun_out/ (launches.csv from the
+gpu__time_duration pass, prof_<tag>.ncu-rep from the --set full pass) into the tracked summaries under profiles/."""
+import csv, collections, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(P, exist_ok=True)
+out = []
+
+# ---- launch list: share of device time per kernel ----
+lp = os.path.join(G, "launches.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(open(lp)) if len(r) > 5]
+    hdr = rows[0]; ik = hdr.index("Kernel Name"); iv = hdr.index("Metric Value"); iu = hdr.index("Metric Unit")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        v = float(r[iv].replace(",", "")); u = r[iu]
+        us = v / 1000.0 if u in ("ns", "nsecond") else v * (1000.0 if u in ("ms", "msecond") else 1.0)
+        name = r[ik].split("(")[0].replace("void ", "").replace("rt::", "")
+        agg[name][0] += 1; agg[name][1] += us
+    tot = sum(a[1] for a in agg.values())
+    out.append("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, `python tools/prof_cmd.py 12`:\n"
+               "C4 800x800, 12 spp, Philox mode; per-launch times are serialised and cold-cache: compare SHARES)\n")
+    out.append("| kernel | launches | total us | share | mean us |\n|---|---|---|---|---|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append("| %s | %d | %.1f | %.1f%% | %.2f |" % (k, a[0], a[1], 100 * a[1] / tot, a[1] / a[0]))
+    out.append("")
+    with open(os.path.join(P, "%s_launches.csv" % tag), "w") as f:
+        w = csv.writer(f); w.writerow(["kernel", "launches", "total_us", "share"])
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            w.writerow([k, a[0], "%.2f" % a[1], "%.4f" % (a[1] / tot)])
+
+# ---- full capture: key metrics per kernel ----
+rep = os.path.join(G, "prof_%s.ncu-rep" % tag)
+traffic = {}
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    open(os.path.join(G, "prof_%s_raw.csv" % tag), "w").write(raw)
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__issue_active.avg.pct", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+            "lts__t_bytes.sum", "l1tex__t_bytes.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
+            "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"]
+    out.append("## `ncu --set full --clock-control none` (same command), first captured launch of each kernel\n")
+    seen = {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("rt::", "")
+        if name in seen:
+            continue
+        seen[name] = r
+    names = list(seen)
+    out.append("| metric | unit | " + " | ".join(names) + " |\n|---|---|" + "---|" * len(names))
+    for k in keys:
+        if k in hdr:
+            i = hdr.index(k)
+            out.append("| %s | %s | %s |" % (k, units[i], " | ".join(seen[n][i] for n in names)))
+    out.append("")
+    def num(x):
+        return float(x.replace(",", ""))
+    for n in names:
+        r = seen[n]
+        def gb(k):
+            i = hdr.index(k); v = num(r[i]); u = units[i]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        traffic[n] = {"dram_bytes": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
+                      "grid": int(num(r[hdr.index("launch__grid_size")])), "block": int(num(r[hdr.index("launch__block_size")])),
+                      "duration_us": num(r[hdr.index("gpu__time_duration.sum")]) / (1000.0 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1.0)}
+    json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
+    # ---- per-source-line attribution ----
+    sass = os.path.join(G, "elf", "all_%s.sass" % tag)
+    if os.path.exists(sass):
+        for kern, pref in (("k_trace", "_ZN2rt7k_traceILi0E"), ("k_shade", "_ZN2rt7k_shadeILi0E")):
+            srccsv = os.path.join(G, "src_%s_%s.csv" % (kern, tag))
+            with open(srccsv, "w") as f:
+                subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], stdout=f, text=True)
+            t = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), srccsv, sass, pref, "30"], stdout=subprocess.PIPE, text=True).stdout
+            out.append("## %s: stall samples and instructions by source line (deepest inline frame outside rt_math.h / rng.h)\n\n```\n%s```\n" % (kern, t))
+open(os.path.join(P, "%s_ncu_summary.md" % tag), "w").write("# ncu summary %s\n\n" % tag + "\n".join(out) + "\n")
+print("wrote profiles/%s_ncu_summary.md" % tag)
