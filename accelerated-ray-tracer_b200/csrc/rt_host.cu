@@ -57,15 +57,78 @@ struct HostDevMath : DevMath {  // rt_scene_export_host only
   float tanf_(float x) override { return tanf(x); }
 };
 
+// ---- device block cache ----
+// cudaMalloc / cudaFree of the path-state buffers (~0.4 GB per scene) cost ~60 ms per build/destroy cycle, as much
+// as the scene build itself. Blocks of 1 MiB and more go back to a per-process free list instead of to the driver
+// and are handed out again to the next scene on the same device (rt_trim_device_cache releases them).
+#include <mutex>
+namespace {
+struct CachedBlock { void* p; size_t bytes; int dev; };
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+size_t g_cache_bytes = 0;
+const size_t kCacheMinBlock = 1u << 20, kCacheMaxTotal = (size_t)8 << 30;
+
+cudaError_t cached_malloc(void** out, size_t bytes) {
+  if (bytes >= kCacheMinBlock) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_cache.size(); ++i)
+      if (g_cache[i].dev == dev && g_cache[i].bytes >= bytes && g_cache[i].bytes <= bytes + bytes / 4 &&
+          (best < 0 || g_cache[i].bytes < g_cache[best].bytes)) best = i;
+    if (best >= 0) {
+      *out = g_cache[best].p;
+      g_cache_bytes -= g_cache[best].bytes;
+      g_cache.erase(g_cache.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  return cudaMalloc(out, bytes);
+}
+// `bytes` must be what the block was allocated with (a cached block may be larger than its last user asked for)
+void cached_free(void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes >= kCacheMinBlock) {
+    int dev = 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess) dev = at.device;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache_bytes + bytes <= kCacheMaxTotal) {
+      g_cache.push_back({p, bytes, dev});
+      g_cache_bytes += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+}  // namespace
+
+extern "C" void rt_trim_device_cache(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& b : g_cache) { cudaSetDevice(b.dev); cudaFree(b.p); }
+  g_cache.clear();
+  g_cache_bytes = 0;
+}
+
 template <class T> struct DBuf {
-  T* p = nullptr; size_t n = 0;
-  cudaError_t alloc(size_t count) { free(); n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+  T* p = nullptr; size_t n = 0; size_t bytes = 0;
+  cudaError_t alloc(size_t count) {
+    free();
+    n = count;
+    size_t want = std::max<size_t>(count, 1) * sizeof(T);
+    // round large requests up to 2 MiB so that a slightly different scene still finds a cached block of the same size
+    if (want >= kCacheMinBlock) want = (want + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    bytes = want;
+    return cached_malloc((void**)&p, want);
+  }
   cudaError_t upload(const std::vector<T>& h) {
     cudaError_t e = alloc(h.size());
     if (e != cudaSuccess || h.empty()) return e;
     return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
   }
-  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void free() { if (p) cached_free(p, bytes); p = nullptr; n = 0; bytes = 0; }
   ~DBuf() { free(); }
 };
 

@@ -54,7 +54,7 @@ class RenderStatsC(C.Structure):
 
 EXPORTS = ["rt_build_scene", "rt_render", "rt_render_stats_get", "rt_readback", "rt_readback_t", "rt_destroy",
            "rt_last_error", "rt_scene_info_get", "rt_scene_export", "rt_scene_export_host", "rt_accum_device_ptr",
-           "rt_resolve", "rt_fb_device_ptr", "rt_write_ppm"]
+           "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm"]
 
 _lib = None
 

@@ -275,9 +275,13 @@ def main():
         Ke = K
         barrier()
         t0 = time.perf_counter()
+        bd = {"build": 0.0, "render_wall": 0.0, "render_device": 0.0, "reduce_readback": 0.0, "destroy": 0.0}
         for i in range(Ke):
+            ta = time.perf_counter()
             s2 = pyrt.Scene(SCENE_ID, NX, NY, texture_dir=tex, device=local)
+            tb = time.perf_counter()
             st = s2.render(spp=spp_all, rng_mode=0, split_mode=1, rank=(W + i) * world + rank, world=passes)
+            tc = time.perf_counter()
             if world > 1:
                 rdist.reduce_sum_to_root(rdist.accum_tensor(s2))
                 torch.cuda.synchronize()
@@ -285,9 +289,13 @@ def main():
                 s2.resolve(total_spp=S * world)
                 pyrt._check(pyrt.lib().rt_readback(s2._h, host_fb.ctypes.data, None, None))
                 d2h += host_fb.nbytes
+            td = time.perf_counter()
             h2d += int(s2.info.h2d_bytes)
             e2e_rays += st.rays
             s2.close()
+            te = time.perf_counter()
+            bd["build"] += (tb - ta) * 1e3; bd["render_wall"] += (tc - tb) * 1e3; bd["render_device"] += st.device_ms
+            bd["reduce_readback"] += (td - tc) * 1e3; bd["destroy"] += (te - td) * 1e3
         barrier()
         dt = (time.perf_counter() - t0) * 1e3
         t = torch.tensor([dt, float(e2e_rays)], dtype=torch.float64, device=dev)
@@ -299,6 +307,7 @@ def main():
             dt, e2e_rays = float(tm[0]), float(ts[1])
         e2e = {"value": round(e2e_rays / dt / 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": h2d // Ke,
                "d2h_bytes_per_step": d2h // Ke if rank == 0 else 0, "ms_per_step": round(dt / Ke, 3),
+               "breakdown_ms_per_step": {k: round(v / Ke, 2) for k, v in bd.items()},
                "what": "per step: rt_build_scene (host generator + H2D scene/texture + device BVH build) + rt_render + "
                        "rt_readback(float fb -> host) + rt_destroy; wall clock, max over ranks"}
 

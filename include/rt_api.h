@@ -104,6 +104,10 @@ int rt_resolve(rt_scene* s, int32_t total_spp, float gamma); /* accum -> framebu
 /* Device address of this rank's framebuffer share (rows_local*nx*3 floats), e.g. for an NCCL gather of tiles. */
 int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
 
+/* rt_destroy keeps device blocks >= 1 MiB in a per-process free list for the next rt_build_scene / rt_render on the
+ * same device (cudaMalloc/cudaFree of the ~0.4 GB path state cost more than a scene build); this releases them. */
+void rt_trim_device_cache(void);
+
 /* PPM writer of the scene functions (main.cu:1212-1221): "P3\n{nx} {ny}\n255\n", rows j = ny-1..0,
  * int(255.99f*c) per channel, no clamp. rgb is a FULL image (ny*nx*3, row 0 = bottom). double_scale != 0
  * reproduces bouncing_spheres' `int(255.99*c)` in double (main.cu:722-724). Returns bytes written or < 0. */

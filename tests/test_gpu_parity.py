@@ -245,3 +245,22 @@ def test_scale_up_c5_bvh_matches_brute_force_ids(pyrt, built):
     o_obj, o_mat, o_t = oracle_py.primary_ids(sd.raw.tobytes(), 320, 180)
     assert np.array_equal(o_obj, obj)
     assert np.array_equal(o_t.view(np.uint32), t.view(np.uint32))
+
+
+def test_cli_ppm_on_stdout_matches_reference_image(pyrt, golden, built):
+    """rt_cli = the reference's main(): P3 PPM on stdout, diagnostics on stderr, exit code 99 on a library error.
+    C1 in reference-RNG mode must print exactly the integers the reference prints (main.cu:715-727, double 255.99)."""
+    import subprocess
+    cli = os.path.join(os.path.dirname(pyrt.LIB_PATH), "rt_cli")
+    g = golden("c1_400x225_10")
+    r = subprocess.run([cli, "--scene", "1", "--nx", "400", "--ny", "225", "--spp", "10", "--rng", "reference"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    tok = r.stdout.split()
+    assert tok[:4] == ["P3", "400", "225", "255"]
+    got = np.array(tok[4:], dtype=np.int64).reshape(225, 400, 3)
+    want = pyrt.to_8bit(g["fb"], double_scale=True)[::-1]  # the PPM starts with the TOP scanline
+    assert np.array_equal(got, want)
+    assert "Mrays/s" in r.stderr
+    bad = subprocess.run([cli, "--scene", "42"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert bad.returncode == 99 and "unknown scene" in bad.stderr
