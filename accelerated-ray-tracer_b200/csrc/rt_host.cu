@@ -58,45 +58,44 @@ struct HostDevMath : DevMath {  // rt_scene_export_host only
 };
 
 // ---- device block cache ----
-// cudaMalloc / cudaFree of the path-state buffers (~0.4 GB per scene) cost ~60 ms per build/destroy cycle, as much
-// as the scene build itself. Blocks of 1 MiB and more go back to a per-process free list instead of to the driver
-// and are handed out again to the next scene on the same device (rt_trim_device_cache releases them).
+// cudaMalloc / cudaFree (and cudaMallocHost / cudaStreamCreate) cost tens to hundreds of milliseconds per scene
+// build/destroy cycle - more than the scene build itself. Device blocks go back to a per-process free list, keyed by
+// (device, canonical size), instead of to the driver, and are handed out again to the next scene on the same device;
+// pinned counters and streams are recycled the same way. rt_trim_device_cache() releases everything.
 #include <mutex>
+#include <unordered_map>
 namespace {
-struct CachedBlock { void* p; size_t bytes; int dev; };
 std::mutex g_cache_mu;
-std::vector<CachedBlock> g_cache;
+std::map<std::pair<int, size_t>, std::vector<void*>> g_cache;  // (device, bytes) -> free blocks
 size_t g_cache_bytes = 0;
-const size_t kCacheMinBlock = 1u << 20, kCacheMaxTotal = (size_t)8 << 30;
+const size_t kCacheMaxTotal = (size_t)16 << 30;
 
+size_t canonical_bytes(size_t want) {  // sizes are rounded so that a slightly different scene finds the same block sizes
+  if (want < 512) return 512;
+  if (want < ((size_t)1 << 20)) { size_t p2 = 512; while (p2 < want) p2 <<= 1; return p2; }
+  return (want + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
+}
 cudaError_t cached_malloc(void** out, size_t bytes) {
-  if (bytes >= kCacheMinBlock) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    int best = -1;
-    for (int i = 0; i < (int)g_cache.size(); ++i)
-      if (g_cache[i].dev == dev && g_cache[i].bytes >= bytes && g_cache[i].bytes <= bytes + bytes / 4 &&
-          (best < 0 || g_cache[i].bytes < g_cache[best].bytes)) best = i;
-    if (best >= 0) {
-      *out = g_cache[best].p;
-      g_cache_bytes -= g_cache[best].bytes;
-      g_cache.erase(g_cache.begin() + best);
+    auto it = g_cache.find(std::make_pair(dev, bytes));
+    if (it != g_cache.end() && !it->second.empty()) {
+      *out = it->second.back();
+      it->second.pop_back();
+      g_cache_bytes -= bytes;
       return cudaSuccess;
     }
   }
   return cudaMalloc(out, bytes);
 }
-// `bytes` must be what the block was allocated with (a cached block may be larger than its last user asked for)
-void cached_free(void* p, size_t bytes) {
+void cached_free(void* p, size_t bytes, int dev) {
   if (!p) return;
-  if (bytes >= kCacheMinBlock) {
-    int dev = 0;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) == cudaSuccess) dev = at.device;
+  {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     if (g_cache_bytes + bytes <= kCacheMaxTotal) {
-      g_cache.push_back({p, bytes, dev});
+      g_cache[std::make_pair(dev, bytes)].push_back(p);
       g_cache_bytes += bytes;
       return;
     }
@@ -105,34 +104,56 @@ void cached_free(void* p, size_t bytes) {
 }
 }  // namespace
 
-extern "C" void rt_trim_device_cache(void) {
-  std::lock_guard<std::mutex> lk(g_cache_mu);
-  for (auto& b : g_cache) { cudaSetDevice(b.dev); cudaFree(b.p); }
-  g_cache.clear();
-  g_cache_bytes = 0;
-}
-
 template <class T> struct DBuf {
-  T* p = nullptr; size_t n = 0; size_t bytes = 0;
+  T* p = nullptr; size_t n = 0; size_t bytes = 0; int dev = 0;
   cudaError_t alloc(size_t count) {
     free();
     n = count;
-    size_t want = std::max<size_t>(count, 1) * sizeof(T);
-    // round large requests up to 2 MiB so that a slightly different scene still finds a cached block of the same size
-    if (want >= kCacheMinBlock) want = (want + (2u << 20) - 1) / (2u << 20) * (2u << 20);
-    bytes = want;
-    return cached_malloc((void**)&p, want);
+    bytes = canonical_bytes(std::max<size_t>(count, 1) * sizeof(T));
+    cudaGetDevice(&dev);
+    return cached_malloc((void**)&p, bytes);
   }
   cudaError_t upload(const std::vector<T>& h) {
     cudaError_t e = alloc(h.size());
     if (e != cudaSuccess || h.empty()) return e;
     return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
   }
-  void free() { if (p) cached_free(p, bytes); p = nullptr; n = 0; bytes = 0; }
+  void free() { if (p) cached_free(p, bytes, dev); p = nullptr; n = 0; bytes = 0; }
   ~DBuf() { free(); }
 };
 
 #define RT_MAX_POOLS 4
+// Per-scene host-side CUDA objects (streams, pinned counter block), recycled across scenes of one device.
+struct HostCtx { int dev = 0; cudaStream_t streams[RT_MAX_POOLS] = {nullptr}; void* pinned = nullptr; };
+namespace {
+std::vector<HostCtx> g_ctx_pool;
+bool ctx_acquire(int dev, size_t pinned_bytes, HostCtx& out) {
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_ctx_pool.size(); ++i)
+      if (g_ctx_pool[i].dev == dev) { out = g_ctx_pool[i]; g_ctx_pool.erase(g_ctx_pool.begin() + i); return true; }
+  }
+  out = HostCtx();
+  out.dev = dev;
+  for (int k = 0; k < RT_MAX_POOLS; ++k) if (cudaStreamCreate(&out.streams[k]) != cudaSuccess) return false;
+  return cudaMallocHost(&out.pinned, pinned_bytes) == cudaSuccess;
+}
+void ctx_release(const HostCtx& c) { std::lock_guard<std::mutex> lk(g_cache_mu); g_ctx_pool.push_back(c); }
+}  // namespace
+
+extern "C" void rt_trim_device_cache(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& kv : g_cache) { cudaSetDevice(kv.first.first); for (void* p : kv.second) cudaFree(p); }
+  g_cache.clear();
+  g_cache_bytes = 0;
+  for (auto& c : g_ctx_pool) {
+    cudaSetDevice(c.dev);
+    for (int k = 0; k < RT_MAX_POOLS; ++k) if (c.streams[k]) cudaStreamDestroy(c.streams[k]);
+    if (c.pinned) cudaFreeHost(c.pinned);
+  }
+  g_ctx_pool.clear();
+}
+
 struct rt_scene {
   int device = 0;
   SceneDesc sd;
@@ -140,7 +161,8 @@ struct rt_scene {
   // flattened scene
   DBuf<DSphere> spheres; DBuf<DQuad> quads; DBuf<DXform> xforms; DBuf<DMedium> media;
   DBuf<DMat> mats; DBuf<DTex> texs; DBuf<DImage> images; DBuf<DTlp> tlp; DBuf<BVH4Node> nodes;
-  std::vector<unsigned char*> image_px;
+  std::vector<DBuf<unsigned char>> image_px;
+  HostCtx ctx; bool has_ctx = false;
   DScene dscene;
   int n_nodes = 0; float bvh_ms = 0.f; uint64_t h2d_bytes = 0;
   // render state
@@ -154,10 +176,7 @@ struct rt_scene {
   size_t slots_cap = 0, pix_cap = 0, accum_valid_pix = 0;
   RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
   ~rt_scene() {
-    for (auto p : image_px) cudaFree(p);
-    if (h_counters) cudaFreeHost(h_counters);
-    if (stream) cudaStreamDestroy(stream);
-    for (int k = 1; k < RT_MAX_POOLS; ++k) if (pool_stream[k]) cudaStreamDestroy(pool_stream[k]);
+    if (has_ctx) ctx_release(ctx);
   }
 };
 
@@ -280,13 +299,15 @@ static int upload_scene(rt_scene* s) {
     texs[i] = d;
   }
   std::vector<DImage> images(sd.img.size());
+  s->image_px.reserve(sd.img.size());  // DBuf is not movable: no reallocation
   uint64_t bytes = 0;
   for (size_t i = 0; i < sd.img.size(); ++i) {
     const HostImage& im = sd.img_data[i];
-    unsigned char* d = nullptr;
-    CU(cudaMalloc(&d, im.px.size()));
-    CU(cudaMemcpy(d, im.px.data(), im.px.size(), cudaMemcpyHostToDevice));
-    s->image_px.push_back(d);
+    s->image_px.emplace_back();
+    DBuf<unsigned char>& ib = s->image_px.back();
+    CU(ib.alloc(im.px.size()));
+    CU(cudaMemcpy(ib.p, im.px.data(), im.px.size(), cudaMemcpyHostToDevice));
+    unsigned char* d = ib.p;
     images[i].data = d; images[i].width = im.width; images[i].height = im.height; images[i].bpp = im.bpp; images[i].pad = 0;
     bytes += im.px.size();
   }
@@ -400,11 +421,11 @@ extern "C" int rt_build_scene(const rt_scene_desc* desc, rt_scene** out) {
   }
   s->rank = reference_leaf_order(s->sd);
   if (upload_scene(s)) { delete s; return 1; }
-  if (cudaStreamCreate(&s->stream) != cudaSuccess) { delete s; return fail("cudaStreamCreate failed"); }
-  s->pool_stream[0] = s->stream;
-  for (int k = 1; k < RT_MAX_POOLS; ++k)
-    if (cudaStreamCreate(&s->pool_stream[k]) != cudaSuccess) { delete s; return fail("cudaStreamCreate failed"); }
-  if (cudaMallocHost(&s->h_counters, RT_MAX_POOLS * sizeof(WaveCounters)) != cudaSuccess) { delete s; return fail("cudaMallocHost failed"); }
+  if (!ctx_acquire(dev, RT_MAX_POOLS * sizeof(WaveCounters), s->ctx)) { delete s; return fail("cudaStreamCreate / cudaMallocHost failed"); }
+  s->has_ctx = true;
+  for (int k = 0; k < RT_MAX_POOLS; ++k) s->pool_stream[k] = s->ctx.streams[k];
+  s->stream = s->pool_stream[0];
+  s->h_counters = (WaveCounters*)s->ctx.pinned;
   *out = s;
   return 0;
 }

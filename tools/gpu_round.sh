@@ -21,7 +21,7 @@ if [[ $WHAT == all || $WHAT == *wavelog* ]]; then
 fi
 if [[ $WHAT == all || $WHAT == *ncu* ]]; then
   timeout 300 python tools/prof_cmd.py 12 > $O/plain.log 2>&1 &&
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches.csv python tools/prof_cmd.py 12 > $O/ncu_launches.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches.csv python tools/prof_cmd.py 12 > $O/ncu_launches.log 2>&1
   echo "launch list rc=$?"; cat $O/plain.log
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_trace|k_shade' -s 16 -c 4 -f -o $O/prof_${TAG:-r01} python tools/prof_cmd.py 12 > $O/ncu_full.log 2>&1
   echo "ncu full rc=$?"; tail -3 $O/ncu_full.log
