@@ -84,6 +84,8 @@ struct Philox {
     return r;
   }
   RT_HD float uniform() { return u32_to_uniform(next()); }
+  // One whole block = four fresh 32-bit words (drops whatever was left of the previous block).
+  RT_HD void next4(uint32_t* o) { block(c0, c1, c2, c3, key0, key1, o); ++c0; have = 0; }
 };
 
 }  // namespace rt

@@ -19,6 +19,20 @@ RT_D void random_in_unit_disk(RNG& g, float& x, float& y) {  // camera.cuh:8-16
   } while (ffma(x, x, fmul(y, y)) >= 1.0f);  // dot(p,p) with p.z = 0
 }
 
+// Philox mode draws the same DISTRIBUTION (uniform in the unit disk) without the rejection loop: one Philox block,
+// no divergence. Only reference-RNG mode has to reproduce the reference's draw sequence.
+#ifndef RT_PHILOX_REJECTION
+template <>
+RT_D void random_in_unit_disk<Philox>(Philox& g, float& x, float& y) {
+  uint32_t o[4];
+  g.next4(o);
+  const float rad = sqrtf(u32_to_uniform(o[0]));
+  float s, c;
+  __sincosf(6.283185307f * u32_to_uniform(o[1]), &s, &c);
+  x = rad * c; y = rad * s;
+}
+#endif
+
 template <class RNG>
 RT_D Ray camera_get_ray(const DCamera& c, float s, float t, RNG& g) {  // camera.cuh:35-47
   float px, py;
@@ -153,6 +167,23 @@ RT_D V3 random_in_unit_sphere(RNG& g) {  // material.cuh:12-18
     if (vsqlen(p) < 1.0f) return p;
   }
 }
+
+// Philox mode: uniform in the unit ball from ONE Philox block, no rejection loop (the reference's loop runs 1.9
+// iterations on average and was 39% of k_shade's instructions at 11.6 active lanes, profiles/r01d): radius = cbrt(u),
+// direction uniform on the sphere. Same distribution, different draw sequence - which only reference-RNG mode must match.
+#ifndef RT_PHILOX_REJECTION
+template <>
+RT_D V3 random_in_unit_sphere<Philox>(Philox& g) {
+  uint32_t o[4];
+  g.next4(o);
+  const float z = ffma(-2.0f, u32_to_uniform(o[1]), 1.0f);
+  const float rxy = sqrtf(fmaxf(0.0f, ffma(-z, z, 1.0f)));
+  float s, c;
+  __sincosf(6.283185307f * u32_to_uniform(o[2]), &s, &c);
+  const float rad = cbrtf(u32_to_uniform(o[0]));
+  return v3(rad * rxy * c, rad * rxy * s, rad * z);
+}
+#endif
 
 // Returns false when the path ends (light, or metal scattering below the surface).
 template <class RNG>
