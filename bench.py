@@ -50,6 +50,19 @@ def texture_dir():
     raise SystemExit("bench: earthmap.ppm not found (run __graft_entry__.build() where /root/reference exists)")
 
 
+def ncu_traffic_per_ray(kernel="k_trace<0>"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the latest committed ncu capture (profiles/*_traffic.json,
+    written by tools/summarize_profile.py), per ray of that launch (grid x block threads, one ray each)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1])).get(kernel)
+    if not d:
+        return None, None
+    return d["dram_bytes"] / (d["grid"] * d["block"]), os.path.basename(files[-1])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -319,6 +332,7 @@ def main():
         trace_s_per_launch = trace_ms / n_launch / 1e3
         achieved = C4_TRACE_BYTES_PER_RAY * rays_per_launch / trace_s_per_launch / 1e9 if trace_ms > 0 else None
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        tpr, tsrc = ncu_traffic_per_ray()
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(span_ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -337,13 +351,16 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 1) if achieved else None,
                          "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": round(tpr * rays_per_launch) if tpr else None,
+                         "traffic_source": ("ncu dram bytes/ray of %s x rays per launch" % tsrc) if tpr else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_ray": C4_TRACE_BYTES_PER_RAY,
                          "rays_per_launch": round(rays_per_launch, 1), "launch_ms": round(trace_ms / n_launch, 5),
                          "share_of_kernel_time": {"k_trace": round(trace_ms / max(trace_ms + shade_ms, 1e-9), 4),
                                                   "k_shade": round(shade_ms / max(trace_ms + shade_ms, 1e-9), 4)},
-                         "note": "the working set of C4 is L2-resident (SURVEY.md §8d): HBM-equivalent bytes of the "
-                                 "reference algorithm; see roofline_fp32 for the ALU roof"},
+                         "note": "achieved = HBM-EQUIVALENT algorithmic bytes of the reference algorithm (SURVEY.md 8d); the scene is "
+                                 "L1/L2-resident, so frac can exceed 1 and the DRAM traffic is only the path state; the kernel is "
+                                 "issue-bound (profiles/README.md), see roofline_fp32 for the ALU roof"},
             "roofline_fp32": {"achieved_tflops": round(value * 1e6 / world * C4_FLOP_PER_RAY / 1e12, 3),
                               "peak_tflops": round(fp32_peak, 1),
                               "frac": round(value * 1e6 / world * C4_FLOP_PER_RAY / 1e12 / fp32_peak, 4),
