@@ -688,7 +688,8 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
 #ifdef RT_STATS
 extern "C" int rt_debug_stats(unsigned long long* out8, int reset) {
   CU(cudaMemcpyFromSymbol(out8, rt::g_stats, 8 * sizeof(unsigned long long)));
-  if (reset) { unsigned long long z[8] = {0}; CU(cudaMemcpyToSymbol(rt::g_stats, z, sizeof(z))); }
+  CU(cudaMemcpyFromSymbol(out8 + 8, rt::g_stats2, 4 * sizeof(unsigned long long)));
+  if (reset) { unsigned long long z[8] = {0}; CU(cudaMemcpyToSymbol(rt::g_stats, z, sizeof(z))); CU(cudaMemcpyToSymbol(rt::g_stats2, z, 4 * sizeof(unsigned long long))); }
   return 0;
 }
 #endif

@@ -255,12 +255,16 @@ RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
 #ifndef RT_LEAFQ
 #define RT_LEAFQ 8         // pending leaves per lane
 #endif
+#ifndef RT_LEAF_WAIT_MAX
+#define RT_LEAF_WAIT_MAX 6   // ... or when this many lanes have finished their traversal and only wait for their leaves (A/B: 4..8 +5%)
+#endif
 #ifndef RT_NODE_MIN
 #define RT_NODE_MIN 3      // leaf phase starts when fewer lanes than this can still expand a node (A/B on C4: 3 beats 1, 8, 12, 16)
 #endif
 struct Hit { float t; int tlp; int face; };
 #ifdef RT_STATS  // diagnostics build only (tools/): per-ray work counters
-__device__ unsigned long long g_stats[8];  // 0 node expansions, 1 sphere tests, 2 geom tests, 3 medium tests, 4 node phases, 5 leaf phases, 6 leaves queued, 7 leaves culled
+__device__ unsigned long long g_stats[8];
+__device__ unsigned long long g_stats2[4];  // per node phase: lanes finished, lanes blocked on a full leaf queue, lanes expanding  // 0 node expansions, 1 sphere tests, 2 geom tests, 3 medium tests, 4 node phases, 5 leaf phases, 6 leaves queued, 7 leaves culled
 #define RT_COUNT(i, n) atomicAdd(&g_stats[i], (unsigned long long)(n))
 #else
 #define RT_COUNT(i, n) do { } while (0)
@@ -294,9 +298,13 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
     const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
     const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, nl > 0);
     if ((mexp | mleaf) == 0u) break;
-    if (mleaf == 0u || __popc(mexp) >= RT_NODE_MIN) {
+    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !have && nl > 0);  // traversal done, leaves pending
+    if (mleaf == 0u || (__popc(mexp) >= RT_NODE_MIN && __popc(mwait) < RT_LEAF_WAIT_MAX)) {
       // ---------------- node phase ----------------
       if ((threadIdx.x & 31) == 0) RT_COUNT(4, 1);
+#ifdef RT_STATS
+      { const unsigned mfin = __ballot_sync(0xFFFFFFFFu, !have && nl == 0); const unsigned mblk = __ballot_sync(0xFFFFFFFFu, have && !can); if ((threadIdx.x & 31) == 0) { atomicAdd(&g_stats2[0], (unsigned long long)__popc(mfin)); atomicAdd(&g_stats2[1], (unsigned long long)__popc(mblk)); atomicAdd(&g_stats2[2], (unsigned long long)__popc(mexp)); } }
+#endif
       if (can) {
         RT_COUNT(0, 1);
         const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
@@ -358,18 +366,20 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
           if (sphere_t<true>(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
         }
       }
-      // quads, boxes, instances
-      const unsigned mgeo = __ballot_sync(0xFFFFFFFFu, [&] { bool any = false; for (int k = 0; k < nl; ++k) { const uint32_t ty = ref_type(lq_ref[k]); any |= (ty != G_SPHERE && ty != G_MEDIUM); } return any; }());
-      if (mgeo) {
-        for (int k = 0; k < nmax; ++k) {
-          if (k < nl) {
-            const uint32_t ty = ref_type(lq_ref[k]);
-            if (ty != G_SPHERE && ty != G_MEDIUM && lq_tn[k] < best.t) {
-              Rec rec; rec.face = 0;
-              RT_COUNT(2, 1);
-              if (geom_hit<false, true>(S, lq_ref[k], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[k], lq_tlp[k], rec.t, rec.face, best);
-            }
+      // quads, boxes, instances: every lane walks ITS geometry leaves with its own cursor, so that the j-th box test of
+      // all lanes runs in the same iteration (a shared position index left 6 of 32 lanes active in the box code)
+      {
+        int kk = 0;
+        while (true) {
+          while (kk < nl && ref_type(lq_ref[kk]) == G_SPHERE || kk < nl && ref_type(lq_ref[kk]) == G_MEDIUM) ++kk;
+          const bool has = kk < nl;
+          if (__ballot_sync(0xFFFFFFFFu, has) == 0u) break;
+          if (has && lq_tn[kk] < best.t) {
+            Rec rec; rec.face = 0;
+            RT_COUNT(2, 1);
+            if (geom_hit<false, true>(S, lq_ref[kk], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[kk], lq_tlp[kk], rec.t, rec.face, best);
           }
+          ++kk;
         }
       }
       // media
