@@ -209,22 +209,6 @@ RT_D bool medium_hit(const DScene& S, const DMedium& m, const Ray& r, float tmin
   return true;
 }
 
-// Top-level object test used by traversal: t only.
-RT_D bool tlp_hit_t(const DScene& S, uint32_t ref, const Ray& r, float tmin, float tmax, float& t_out) {
-  const uint32_t ty = ref_type(ref), ix = ref_index(ref);
-  if (ty == G_SPHERE) {
-    V3 cc;
-    return sphere_t(S.spheres[ix], r, tmin, tmax, t_out, cc);
-  } else if (ty == G_MEDIUM) {
-    return medium_hit(S, S.media[ix], r, tmin, tmax, t_out);
-  } else {
-    Rec rec;
-    if (!geom_hit<false>(S, ref, r, tmin, tmax, false, rec)) return false;
-    t_out = rec.t;
-    return true;
-  }
-}
-
 // Is the object's own interval test inclusive at tmax (quad: t > tmax rejects) or exclusive (sphere: t < tmax)?
 RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
   while (ref_type(ref) == G_XFORM) ref = S.xforms[ref_index(ref)].child;
