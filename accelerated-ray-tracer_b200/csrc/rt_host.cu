@@ -590,7 +590,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     for (int k = 0; k < n_pools; ++k) {
       G[k] = (Pp[k].n_slots + B - 1) / B;
       Gs[k] = (Pp[k].n_slots + 32 * Q_COUNT + B - 1) / B;
-      Gt[k] = (Pp[k].n_slots + 32 * Q_COUNT + RT_TBLOCK * RT_RAYS_PER_LANE - 1) / (RT_TBLOCK * RT_RAYS_PER_LANE);
+      Gt[k] = (Pp[k].n_slots + 32 * Q_COUNT + RT_TBLOCK - 1) / RT_TBLOCK;
       if (ref_rng) k_init<RNG_REFERENCE><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
       else k_init<RNG_PHILOX><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
       ++launches;

@@ -266,49 +266,21 @@ RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int 
   if (take) { best.t = t; best.tlp = (int)tlp; best.face = face; }
 }
 
-// Ray source of trace_rays. A lane may be given several rays, one after the other: a lane whose ray is finished
-// fetches its next one while the other lanes of the warp are still working, instead of idling until the slowest lane
-// of the warp is done (27% of the node-phase lane slots were such finished lanes with one ray per lane, stats build).
-//   bool more()            this lane may have another ray
-//   bool fetch(Ray& r)     next ray of this lane, false when there is none
-//   void commit(Hit h)     result of the lane's current ray
-#ifndef RT_FETCH_MIN
-#define RT_FETCH_MIN 8      // lanes that must be waiting for a new ray before the warp takes a (divergent) fetch step
-#endif
-template <class Feeder>
-RT_D void trace_rays(const DScene& S, Feeder& F, float tmin, float tmax0, unsigned int* overflow) {
-  Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
+RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
   Hit best; best.t = tmax0; best.tlp = -1; best.face = 0;
-  float ix = 1.f, iy = 1.f, iz = 1.f;  // 1.0f / direction, aabb.cuh:48
+  const float ix = frcp(r.d.x), iy = frcp(r.d.y), iz = frcp(r.d.z);  // 1.0f / direction, aabb.cuh:48
   // float4 index of the NEAR plane vector of each axis inside a node (lox 0, loy 1, loz 2, hix 3, hiy 4, hiz 5)
-  int onx = 0, ony = 1, onz = 2;
+  const int onx = ix < 0.0f ? 3 : 0, ony = iy < 0.0f ? 4 : 1, onz = iz < 0.0f ? 5 : 2;
   uint32_t stack[RT_STACK];  // interior nodes only
   uint32_t lq_ref[RT_LEAFQ], lq_tlp[RT_LEAFQ];
   float lq_tn[RT_LEAFQ];
   int sp = 0, nl = 0;
   uint32_t cur = 0;
-  bool have = false, busy = false;
+  bool have = active;
   while (true) {
     const bool can = have && nl <= RT_LEAFQ - 4;
     const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
     const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, nl > 0);
-    // ---- fetch step: finished lanes hand in their result and take their next ray ----
-    const bool fin = busy && !have && nl == 0;
-    const bool want = (fin || !busy) && F.more();
-    const unsigned mwant = __ballot_sync(0xFFFFFFFFu, want);
-    if (mwant != 0u && (__popc(mwant) >= RT_FETCH_MIN || (mexp | mleaf) == 0u)) {
-      if (want) {
-        if (fin) F.commit(best);
-        busy = F.fetch(r);
-        if (busy) {
-          best.t = tmax0; best.tlp = -1; best.face = 0;
-          ix = frcp(r.d.x); iy = frcp(r.d.y); iz = frcp(r.d.z);
-          onx = ix < 0.0f ? 3 : 0; ony = iy < 0.0f ? 4 : 1; onz = iz < 0.0f ? 5 : 2;
-          sp = 0; cur = 0; have = true;
-        }
-      }
-      continue;
-    }
     if ((mexp | mleaf) == 0u) break;
     const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !have && nl > 0);  // traversal done, leaves pending
     if (mleaf == 0u || (__popc(mexp) >= RT_NODE_MIN && __popc(mwait) < RT_LEAF_WAIT_MAX)) {
@@ -408,21 +380,7 @@ RT_D void trace_rays(const DScene& S, Feeder& F, float tmin, float tmax0, unsign
       nl = 0;
     }
   }
-  if (busy) F.commit(best);  // every busy lane is finished here
-}
-
-// One ray per lane (k_aov, and the RT_RAYS_PER_LANE = 1 build of k_trace).
-struct SingleRayFeeder {
-  Ray ray; bool pending; Hit hit;
-  RT_D bool more() const { return pending; }
-  RT_D bool fetch(Ray& r) { if (!pending) return false; pending = false; r = ray; return true; }
-  RT_D void commit(const Hit& h) { hit = h; }
-};
-RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
-  SingleRayFeeder F;
-  F.ray = r; F.pending = active; F.hit.t = tmax0; F.hit.tlp = -1; F.hit.face = 0;
-  trace_rays(S, F, tmin, tmax0, overflow);
-  return F.hit;
+  return best;
 }
 
 }  // namespace rt

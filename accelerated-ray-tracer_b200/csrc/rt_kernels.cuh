@@ -185,61 +185,6 @@ __global__ void __launch_bounds__(RT_BLOCK) k_init(RenderParams P, PathArrays A)
   }
 }
 
-#ifndef RT_RAYS_PER_LANE
-#define RT_RAYS_PER_LANE 2   // rays a k_trace lane works through one after the other (see trace_rays)
-#endif
-// Block-aggregated reservation of `count` consecutive items per thread: ONE global atomic per block.
-template <int NW, class T>
-RT_D T block_reserve_n(T* counter, int count, int* s_cnt /*[NW]*/, T* s_base) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int x = count;  // inclusive warp scan
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
-  if (lane == 31) s_cnt[warp] = x;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
-    *s_base = tot > 0 ? atomicAdd(counter, (T)tot) : (T)0;
-  }
-  __syncthreads();
-  const T pos = *s_base + (T)(s_cnt[warp] + x - count);
-  __syncthreads();
-  return pos;
-}
-
-// Ray source of k_trace: lane `lane` of a warp owns entries base + r * 32 + lane (r = 0 .. RT_RAYS_PER_LANE - 1) of the
-// order array and traces them one after the other.
-struct TraceFeeder {
-  const PathArrays& A; const DTlp* tlp;
-  int base, lane, order_len;
-  int r, cur_slot, cur_r;
-  unsigned qs;  // 4 bits per ray: shade-queue class + 1 of the finished rays (0 = no ray)
-  RT_D TraceFeeder(const PathArrays& a, const DTlp* t, int b, int l, int n) : A(a), tlp(t), base(b), lane(l), order_len(n), r(0), cur_slot(-1), cur_r(0), qs(0u) {}
-  RT_D bool more() const { return r < RT_RAYS_PER_LANE && base + r * 32 + lane < order_len; }
-  RT_D bool fetch(Ray& ray) {
-    while (r < RT_RAYS_PER_LANE) {
-      const int rr = r++;
-      const int e = base + rr * 32 + lane;
-      if (e >= order_len) { r = RT_RAYS_PER_LANE; return false; }
-      const int slot = A.order[e];
-      if (slot < 0) continue;                               // padding between two shade queues
-      if (__float_as_int(A.thr[slot].w) < 0) continue;      // dead slot (the work ran out)
-      const float4 o = A.ray_o[slot], d = A.ray_d[slot];
-      ray.o = v3(o.x, o.y, o.z); ray.d = v3(d.x, d.y, d.z); ray.tm = o.w;
-      cur_slot = slot; cur_r = rr;
-      return true;
-    }
-    return false;
-  }
-  RT_D void commit(const Hit& h) {
-    A.hit[cur_slot] = make_float2(h.t, __int_as_float(h.tlp < 0 ? -1 : (h.tlp | (h.face << 28))));
-    const int q = h.tlp < 0 ? (int)Q_MISS : tlp[h.tlp].queue;
-    qs |= (unsigned)(q + 1) << (4 * cur_r);
-  }
-};
-
 template <int MODE>
 __global__ void __launch_bounds__(RT_TBLOCK) k_trace(DScene S, RenderParams P, PathArrays A, int* __restrict__ queues,
                                                      WaveCounters* C, int parity) {
@@ -247,73 +192,67 @@ __global__ void __launch_bounds__(RT_TBLOCK) k_trace(DScene S, RenderParams P, P
   __shared__ unsigned long long s_wbase;
   __shared__ int s_q[RT_TWARPS][Q_COUNT];
   __shared__ int s_qbase[Q_COUNT];
-  // Thread -> slots through the previous wave's queue layout (`order`): paths that hit the same material class sit
-  // next to each other, and the primary rays regenerated behind the miss / light queues come out in pixel order,
-  // which keeps warps far more coherent than slot order (measured: 0.32 ms vs 0.53 ms per 1 Mi-ray wave on C4).
-  // No early exit: trace_rays is warp-wide, regeneration and binning are block-wide.
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int base = (blockIdx.x * RT_TWARPS + warp) * 32 * RT_RAYS_PER_LANE;
-  const int order_len = C->order_len;
+  // Thread -> slot through the previous wave's queue layout: paths that hit the same material class sit next to
+  // each other, and the primary rays regenerated behind the miss / light queues come out in pixel order, which
+  // keeps warps far more coherent than slot order (measured: 0.32 ms vs 0.53 ms per 1 Mi-ray wave on C4).
+  // No early exit: closest_hit is warp-wide, the binning block-wide.
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int slot = -1;
+  if (gid < C->order_len) slot = A.order[gid];
+  const bool in_range = slot >= 0;
+  int state = SLOT_DEAD;
+  if (in_range) state = __float_as_int(A.thr[slot].w);
+  bool active = state >= 0;
+  Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
   // ---- path regeneration (main.cu:119-123): a slot whose sample has ended takes the next one ----
-  int n_need = 0;
-#pragma unroll
-  for (int rr = 0; rr < RT_RAYS_PER_LANE; ++rr) {
-    const int e = base + rr * 32 + lane;
-    const int slot = e < order_len ? A.order[e] : -1;
-    if (slot >= 0 && __float_as_int(A.thr[slot].w) == SLOT_NEEDS_SAMPLE) ++n_need;
-  }
+  const bool need = state == SLOT_NEEDS_SAMPLE;
   if constexpr (MODE == RNG_PHILOX) {
-    unsigned long long w = block_reserve_n<RT_TWARPS>(A.next_work, n_need, s_cnt, &s_wbase);
-    if (n_need > 0) {
-#pragma unroll
-      for (int rr = 0; rr < RT_RAYS_PER_LANE; ++rr) {
-        const int e = base + rr * 32 + lane;
-        const int slot = e < order_len ? A.order[e] : -1;
-        if (slot < 0 || __float_as_int(A.thr[slot].w) != SLOT_NEEDS_SAMPLE) continue;
-        if (w < (unsigned long long)P.work_total) {
-          int lpix, sample;
-          work_to_pixel_sample(P, w, lpix, sample);
-          const SlotInfo si = pixel_info(P, lpix);
-          Philox g;
-          rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-          start_sample(S, P, A, slot, si, sample, g);
-        } else {
-          A.thr[slot].w = __int_as_float((int)SLOT_DEAD);
-        }
-        ++w;
+    const unsigned long long w = block_reserve<RT_TWARPS>(A.next_work, need, s_cnt, &s_wbase);
+    if (need) {
+      if (w < (unsigned long long)P.work_total) {
+        int lpix, sample;
+        work_to_pixel_sample(P, w, lpix, sample);
+        const SlotInfo si = pixel_info(P, lpix);
+        Philox g;
+        rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
+        r = start_sample(S, P, A, slot, si, sample, g);
+        active = true;
+      } else {
+        A.thr[slot].w = __int_as_float((int)SLOT_DEAD);
       }
     }
   } else {
-#pragma unroll
-    for (int rr = 0; rr < RT_RAYS_PER_LANE; ++rr) {
-      const int e = base + rr * 32 + lane;
-      const int slot = e < order_len ? A.order[e] : -1;
-      if (slot < 0 || __float_as_int(A.thr[slot].w) != SLOT_NEEDS_SAMPLE) continue;
+    if (need) {
       const int sample = __float_as_int(A.rad[slot].w) + 1;
       if (sample < P.sample_base + P.sample_count) {
         const SlotInfo si = pixel_info(P, slot);
         Xorwow g;
         rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-        start_sample(S, P, A, slot, si, sample, g);
+        r = start_sample(S, P, A, slot, si, sample, g);
         rng_store(g, A, P, slot);
+        active = true;
       } else {
         A.thr[slot].w = __int_as_float((int)SLOT_DEAD);
       }
     }
   }
-  // ---- closest hit of every live ray of this warp (main.cu:57) ----
-  TraceFeeder F(A, S.tlp, base, lane, order_len);
-  trace_rays(S, F, P.tmin, FLT_MAX, &C->overflow);
+  if (active && !need) {
+    const float4 o = A.ray_o[slot], d = A.ray_d[slot];
+    r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+  }
+  // ---- closest hit (main.cu:57) ----
+  const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
+  int q = -1;
+  if (active) {
+    A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp < 0 ? -1 : (h.tlp | (h.face << 28))));
+    q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
+  }
   // ---- bin by material class: per-warp counts per class in shared memory, ONE global atomic per class per block ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane < Q_COUNT) s_q[warp][lane] = 0;
   __syncwarp();
-#pragma unroll
-  for (int rr = 0; rr < RT_RAYS_PER_LANE; ++rr) {
-    const int q = (int)((F.qs >> (4 * rr)) & 15u) - 1;
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, q);
-    if (q >= 0 && lane == __ffs(peers) - 1) s_q[warp][q] += __popc(peers);
-    __syncwarp();
-  }
+  const unsigned peers = __match_any_sync(0xFFFFFFFFu, q);
+  if (q >= 0 && lane == __ffs(peers) - 1) s_q[warp][q] = __popc(peers);
   __syncthreads();
   if (threadIdx.x < Q_COUNT) {
     int tot = 0;
@@ -322,18 +261,7 @@ __global__ void __launch_bounds__(RT_TBLOCK) k_trace(DScene S, RenderParams P, P
     s_qbase[threadIdx.x] = tot > 0 ? atomicAdd(&C->n_queue[parity][threadIdx.x], tot) : 0;
   }
   __syncthreads();
-#pragma unroll
-  for (int rr = 0; rr < RT_RAYS_PER_LANE; ++rr) {
-    const int q = (int)((F.qs >> (4 * rr)) & 15u) - 1;
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, q);
-    if (q >= 0) {
-      const int e = base + rr * 32 + lane;
-      queues[(size_t)q * P.n_slots + s_qbase[q] + s_q[warp][q] + __popc(peers & ((1u << lane) - 1u))] = A.order[e];
-    }
-    __syncwarp();
-    if (q >= 0 && lane == __ffs(peers) - 1) s_q[warp][q] += __popc(peers);
-    __syncwarp();
-  }
+  if (q >= 0) queues[(size_t)q * P.n_slots + s_qbase[q] + s_q[warp][q] + __popc(peers & ((1u << lane) - 1u))] = slot;
 }
 
 template <int MODE>
