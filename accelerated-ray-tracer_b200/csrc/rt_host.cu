@@ -305,9 +305,12 @@ static int upload_scene(rt_scene* s) {
     const HostImage& im = sd.img_data[i];
     s->image_px.emplace_back();
     DBuf<unsigned char>& ib = s->image_px.back();
-    CU(ib.alloc(im.px.size()));
-    CU(cudaMemcpy(ib.p, im.px.data(), im.px.size(), cudaMemcpyHostToDevice));
-    unsigned char* d = ib.p;
+    unsigned char* d = nullptr;  // no pixels: the texture renders (0,1,1) like the reference's invalid DeviceImage
+    if (!im.px.empty()) {
+      CU(ib.alloc(im.px.size()));
+      CU(cudaMemcpy(ib.p, im.px.data(), im.px.size(), cudaMemcpyHostToDevice));
+      d = ib.p;
+    }
     images[i].data = d; images[i].width = im.width; images[i].height = im.height; images[i].bpp = im.bpp; images[i].pad = 0;
     bytes += im.px.size();
   }
@@ -401,6 +404,18 @@ static int upload_scene(rt_scene* s) {
 // ---- C ABI ----
 extern "C" const char* rt_last_error(void) { return g_err.c_str(); }
 
+static int finish_build(rt_scene* s, int dev, rt_scene** out) {
+  s->rank = reference_leaf_order(s->sd);
+  if (upload_scene(s)) { delete s; return 1; }
+  if (!ctx_acquire(dev, RT_MAX_POOLS * sizeof(WaveCounters), s->ctx)) { delete s; return fail("cudaStreamCreate / cudaMallocHost failed"); }
+  s->has_ctx = true;
+  for (int k = 0; k < RT_MAX_POOLS; ++k) s->pool_stream[k] = s->ctx.streams[k];
+  s->stream = s->pool_stream[0];
+  s->h_counters = (WaveCounters*)s->ctx.pinned;
+  *out = s;
+  return 0;
+}
+
 extern "C" int rt_build_scene(const rt_scene_desc* desc, rt_scene** out) {
   if (!desc || !out) return fail("rt_build_scene: null argument");
   *out = nullptr;
@@ -419,15 +434,26 @@ extern "C" int rt_build_scene(const rt_scene_desc* desc, rt_scene** out) {
     if (!err.empty()) { delete s; return fail("rt_build_scene: " + err); }
     if (!dm.ok) { delete s; return fail("rt_build_scene: device math service failed"); }
   }
-  s->rank = reference_leaf_order(s->sd);
-  if (upload_scene(s)) { delete s; return 1; }
-  if (!ctx_acquire(dev, RT_MAX_POOLS * sizeof(WaveCounters), s->ctx)) { delete s; return fail("cudaStreamCreate / cudaMallocHost failed"); }
-  s->has_ctx = true;
-  for (int k = 0; k < RT_MAX_POOLS; ++k) s->pool_stream[k] = s->ctx.streams[k];
-  s->stream = s->pool_stream[0];
-  s->h_counters = (WaveCounters*)s->ctx.pinned;
-  *out = s;
-  return 0;
+  return finish_build(s, dev, out);
+}
+
+// Build from a caller-made scene description (the flat SD format of rt_scene_desc.h): the generic path behind the
+// scene vocabulary. A scene built this way from rt_scene_export's output renders bit-identically to the original.
+extern "C" int rt_build_scene_sd(const void* sd, size_t sd_bytes, const unsigned char* const* image_pixels, int32_t n_images,
+                                 int32_t device, rt_scene** out) {
+  if (!sd || !out) return fail("rt_build_scene_sd: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("rt_build_scene_sd: no CUDA device (this library has no CPU path)");
+  int dev = device;
+  if (dev < 0) { CU(cudaGetDevice(&dev)); }
+  CU(cudaSetDevice(dev));
+  rt_scene* s = new rt_scene();
+  s->device = dev;
+  std::string err = sd_deserialize(sd, sd_bytes, image_pixels, n_images, s->sd);
+  if (!err.empty()) { delete s; return fail("rt_build_scene_sd: " + err); }
+  return finish_build(s, dev, out);
 }
 
 extern "C" void rt_destroy(rt_scene* s) {

@@ -346,4 +346,66 @@ std::string sd_serialize(const SceneDesc& sd) {
   return s;
 }
 
+// Inverse of sd_serialize, with validation of every index (the buffer comes from the caller). Image pixels are not
+// part of the SD: `images[i]` points to width*height*bpp bytes for image i (or is null: the texture renders cyan
+// like the reference's invalid DeviceImage, texture.cuh:52).
+std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* const* images, int n_images, SceneDesc& sd) {
+  if (!buf || bytes < sizeof(rt_sd_header)) return "scene description too short";
+  rt_sd_header h;
+  memcpy(&h, buf, sizeof(h));
+  if (h.magic != RT_SD_MAGIC) return "bad scene description magic";
+  if (h.n_tex < 0 || h.n_mat < 0 || h.n_obj < 0 || h.n_top < 0 || h.n_img < 0 || h.nx <= 0 || h.ny <= 0) return "bad scene description header";
+  const size_t need = sizeof(h) + (size_t)h.n_tex * sizeof(rt_texture_desc) + (size_t)h.n_mat * sizeof(rt_material_desc) +
+                      (size_t)h.n_obj * sizeof(rt_object_desc) + (size_t)h.n_top * sizeof(int) + (size_t)h.n_img * sizeof(rt_image_desc);
+  if (bytes < need) return "scene description truncated";
+  const char* p = (const char*)buf + sizeof(h);
+  sd = SceneDesc();
+  sd.scene_id = h.scene_id; sd.nx = h.nx; sd.ny = h.ny; sd.cam = h.cam;
+  sd.tex.resize(h.n_tex); memcpy(sd.tex.data(), p, sd.tex.size() * sizeof(rt_texture_desc)); p += sd.tex.size() * sizeof(rt_texture_desc);
+  sd.mat.resize(h.n_mat); memcpy(sd.mat.data(), p, sd.mat.size() * sizeof(rt_material_desc)); p += sd.mat.size() * sizeof(rt_material_desc);
+  sd.obj.resize(h.n_obj); memcpy(sd.obj.data(), p, sd.obj.size() * sizeof(rt_object_desc)); p += sd.obj.size() * sizeof(rt_object_desc);
+  sd.top.resize(h.n_top); memcpy(sd.top.data(), p, sd.top.size() * sizeof(int)); p += sd.top.size() * sizeof(int);
+  sd.img.resize(h.n_img); memcpy(sd.img.data(), p, sd.img.size() * sizeof(rt_image_desc));
+  sd.default_nx = h.nx; sd.default_ny = h.ny; sd.default_spp = 10;
+  for (const auto& t : sd.tex) {
+    if (t.kind < RT_TEX_SOLID || t.kind > RT_TEX_UV_OFFSET) return "texture kind out of range";
+    if (t.kind == RT_TEX_CHECKER && (t.even < 0 || t.even >= h.n_tex || t.odd < 0 || t.odd >= h.n_tex)) return "checker child out of range";
+    if (t.kind == RT_TEX_UV_OFFSET && (t.even < 0 || t.even >= h.n_tex)) return "uv_offset base out of range";
+    if (t.kind == RT_TEX_IMAGE && (t.image < 0 || t.image >= h.n_img)) return "image id out of range";
+  }
+  for (const auto& m : sd.mat) {
+    if (m.kind < RT_MAT_LAMBERTIAN || m.kind > RT_MAT_ISOTROPIC) return "material kind out of range";
+    if (m.tex >= h.n_tex) return "material texture out of range";
+    if ((m.kind == RT_MAT_ISOTROPIC) && m.tex < 0) return "isotropic needs a texture";
+  }
+  for (int i = 0; i < h.n_obj; ++i) {
+    const rt_object_desc& o = sd.obj[i];
+    if (o.kind < RT_OBJ_SPHERE || o.kind > RT_OBJ_MEDIUM) return "object kind out of range";
+    const bool leaf = o.kind == RT_OBJ_SPHERE || o.kind == RT_OBJ_QUAD;
+    if ((leaf || o.kind == RT_OBJ_MEDIUM) && (o.mat < 0 || o.mat >= h.n_mat)) return "object material out of range";
+    if (o.kind == RT_OBJ_BOX) {
+      if (o.child < 0 || o.child + 6 > h.n_obj) return "box faces out of range";
+      for (int f = 0; f < 6; ++f) if (sd.obj[o.child + f].kind != RT_OBJ_QUAD) return "box face is not a quad";
+    }
+    if (o.kind == RT_OBJ_TRANSLATE || o.kind == RT_OBJ_ROTATE_Y || o.kind == RT_OBJ_MEDIUM) {
+      // children are created before their wrappers (like the reference's `new` order): no cycles, bounded depth
+      if (o.child < 0 || o.child >= i) return "wrapper child must precede the wrapper";
+      if (sd.obj[o.child].kind == RT_OBJ_MEDIUM) return "a medium cannot be wrapped";
+      int depth = 0;
+      for (int c = i; sd.obj[c].kind == RT_OBJ_TRANSLATE || sd.obj[c].kind == RT_OBJ_ROTATE_Y || sd.obj[c].kind == RT_OBJ_MEDIUM; c = sd.obj[c].child)
+        if (sd.obj[c].kind != RT_OBJ_MEDIUM && ++depth > 4) return "more than 4 nested instance wrappers";
+    }
+  }
+  for (int t : sd.top) if (t < 0 || t >= h.n_obj) return "top-level object out of range";
+  sd.img_data.resize(h.n_img);
+  for (int i = 0; i < h.n_img; ++i) {
+    const rt_image_desc& d = sd.img[i];
+    HostImage& im = sd.img_data[i];
+    im.width = d.width; im.height = d.height; im.bpp = d.bpp;
+    if (images && i < n_images && images[i] && d.width > 0 && d.height > 0 && d.bpp >= 3)
+      im.px.assign(images[i], images[i] + (size_t)d.width * d.height * d.bpp);
+  }
+  return "";
+}
+
 }  // namespace rt

@@ -118,5 +118,6 @@ std::vector<int> reference_leaf_order(const SceneDesc& sd, int limit = 20000);
 
 bool load_ppm(const std::string& path, HostImage& out);
 std::string sd_serialize(const SceneDesc& sd);  // binary SD file image
+std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* const* images, int n_images, SceneDesc& sd);  // "" or an error
 
 }  // namespace rt

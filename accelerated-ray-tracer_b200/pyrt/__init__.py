@@ -52,7 +52,7 @@ class RenderStatsC(C.Structure):
                 ("profiled_waves", C.c_int32), ("trace_ms", C.c_double), ("shade_ms", C.c_double)]
 
 
-EXPORTS = ["rt_build_scene", "rt_render", "rt_render_stats_get", "rt_readback", "rt_readback_t", "rt_destroy",
+EXPORTS = ["rt_build_scene", "rt_build_scene_sd", "rt_render", "rt_render_stats_get", "rt_readback", "rt_readback_t", "rt_destroy",
            "rt_last_error", "rt_scene_info_get", "rt_scene_export", "rt_scene_export_host", "rt_accum_device_ptr",
            "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm"]
 
@@ -69,6 +69,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.rt_last_error.restype = C.c_char_p
         L.rt_build_scene.argtypes = [C.POINTER(SceneDescC), C.POINTER(C.c_void_p)]
+        L.rt_build_scene_sd.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.rt_render.argtypes = [C.c_void_p, C.POINTER(RenderParamsC), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.rt_render_stats_get.argtypes = [C.c_void_p, C.POINTER(RenderStatsC)]
         L.rt_readback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -236,13 +237,21 @@ def SD_peek_ntop(L, d):
 class Scene:
     """A scene resident on one GPU: generator -> H2D -> device BVH build (rt_build_scene)."""
 
-    def __init__(self, scene_id, nx=0, ny=0, grid_half=0, texture_dir=None, device=-1):
+    def __init__(self, scene_id=0, nx=0, ny=0, grid_half=0, texture_dir=None, device=-1, sd=None, images=()):
+        """scene_id 1..10: one of the reference's generators. sd = bytes of a scene description (rt_scene_desc.h)
+        instead: the generic path (rt_build_scene_sd); images = decoded uint8 arrays for its image textures."""
         L = lib()
         self._h = C.c_void_p()
-        td = (texture_dir or default_texture_dir()).encode()
-        self._td = td
-        d = SceneDescC(scene_id, nx, ny, grid_half, device, td)
-        _check(L.rt_build_scene(C.byref(d), C.byref(self._h)))
+        if sd is not None:
+            raw = bytes(sd)
+            imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+            arr = (C.c_void_p * max(len(imgs), 1))(*[im.ctypes.data for im in imgs])
+            _check(L.rt_build_scene_sd(raw, len(raw), arr, len(imgs), device, C.byref(self._h)))
+        else:
+            td = (texture_dir or default_texture_dir()).encode()
+            self._td = td
+            d = SceneDescC(scene_id, nx, ny, grid_half, device, td)
+            _check(L.rt_build_scene(C.byref(d), C.byref(self._h)))
         info = SceneInfoC()
         _check(L.rt_scene_info_get(self._h, C.byref(info)))
         self.info = info

@@ -77,6 +77,13 @@ typedef struct rt_render_stats {
 
 /* create_world_*<<<1,1>>> + texture upload (main.cu:1186-1204): host generator -> H2D -> device BVH build. */
 int rt_build_scene(const rt_scene_desc* desc, rt_scene** out);
+/* The same from a caller-made scene: `sd` is a scene description in the flat format of rt_scene_desc.h (what the
+ * reference's device-side `new sphere(...) / new quad(...) / ...; new bvh_node(d_list, 0, n)` would have built, e.g. the
+ * output of rt_scene_export or of the SceneBuilder in csrc/scene_builder.h); image_pixels[i] = decoded 8-bit pixels of
+ * image i (width*height*bpp bytes, may be NULL). Every index in the buffer is validated. The scene function's host
+ * parameters (spp, background) are not part of an SD: pass them in rt_render_params (defaults: 10 spp, black). */
+int rt_build_scene_sd(const void* sd, size_t sd_bytes, const unsigned char* const* image_pixels, int32_t n_images,
+                      int32_t device, rt_scene** out);
 /* render_init + render (main.cu:1207-1209). device_ms / rays may be NULL. */
 int rt_render(rt_scene* s, const rt_render_params* p, double* device_ms, uint64_t* rays);
 int rt_render_stats_get(rt_scene* s, rt_render_stats* out);
