@@ -235,7 +235,9 @@ RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
 //                time instead of interleaving node steps, sphere, box and medium code lane by lane.
 // (First version: leaf tests inline in the node loop ran at 2-6 active lanes per instruction on the
 // Book-2 final scene, profiles/r01.)
+#ifndef RT_STACK
 #define RT_STACK 48
+#endif
 #ifndef RT_LEAFQ
 #define RT_LEAFQ 8         // pending leaves per lane
 #endif

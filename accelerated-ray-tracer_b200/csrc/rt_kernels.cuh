@@ -185,8 +185,11 @@ __global__ void __launch_bounds__(RT_BLOCK) k_init(RenderParams P, PathArrays A)
   }
 }
 
+#ifndef RT_TRACE_MINB
+#define RT_TRACE_MINB 4     // resident k_trace blocks per SM the kernel is compiled for (64 registers)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(RT_TBLOCK) k_trace(DScene S, RenderParams P, PathArrays A, int* __restrict__ queues,
+__global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, RenderParams P, PathArrays A, int* __restrict__ queues,
                                                      WaveCounters* C, int parity) {
   __shared__ int s_cnt[RT_TWARPS];
   __shared__ unsigned long long s_wbase;

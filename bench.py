@@ -237,6 +237,7 @@ def main():
         st = sc.render(spp=spp_all, rng_mode=0, split_mode=1, rank=i * world + rank, world=passes, profile=profile)
         if world > 1:
             rdist.reduce_sum_to_root(rdist.accum_tensor(sc))  # NCCL reduce over NVLink: the image of this pass on rank 0
+            torch.cuda.current_stream().synchronize()  # the next pass overwrites the accumulation buffer
         return st
 
     for i in range(W):
