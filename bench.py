@@ -215,6 +215,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench: no CUDA device (the render path has no CPU fallback)")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT, next to the one JSON line
     world, rank, local = rdist.init_process_group("nccl")
     if world != args.gpus:
         raise SystemExit("bench: --gpus %d but WORLD_SIZE=%d (launch N>1 with torchrun)" % (args.gpus, world))
