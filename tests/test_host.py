@@ -194,3 +194,15 @@ def test_bench_reference_arm_contract():
                         "--warmup", "0"], env=dict(os.environ, RANK="1", WORLD_SIZE="2"), stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_c5_grid_generator_sizes(pyrt):
+    """C5 scale-up: GRID_MIN/MAX (main.cu:140-141) generalised by grid_half; (2G)^2 grid cells + ground + 3 big spheres."""
+    for g in (11, 20, 50):
+        sd, rank = pyrt.export_host(1, 64, 36, grid_half=g)
+        assert len(sd.top) == 4 * g * g + 4
+        assert sorted(rank.tolist()) == list(range(len(sd.top)))
+        kinds = sd.obj["kind"][sd.top]
+        assert (kinds == 0).all()  # spheres only
+        moving = (np.abs(sd.obj["dc"][sd.top]).sum(axis=1) > 0).mean()
+        assert 0.6 < moving < 0.9  # ~80% of the grid is diffuse (moving), SURVEY §8a7
