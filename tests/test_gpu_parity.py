@@ -319,3 +319,17 @@ def test_scene_from_exported_description_renders_identically(pyrt):
     trunc = sd.raw.tobytes()[:-40]
     with pytest.raises(pyrt.RtError):
         pyrt.Scene(sd=trunc)
+
+
+def test_two_gpu_paths_match_single_gpu(pyrt):
+    """Real multi-GPU run (needs >= 2 visible GPUs, else skipped; the 1-GPU emulation above always runs): torchrun x 2,
+    NCCL gather of tile-split shares bit-identical to 1 GPU, NCCL reduce of spp-split sums equal to rounding, and
+    rt_cli --gpus 2 (one process, one host thread per GPU) printing the reference's integers."""
+    import subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (evidence of the last 2-GPU run: profiles/r01f_dist_check_n2.txt)")
+    root = os.path.dirname(os.path.dirname(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "dist_check.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "dist_check: OK" in r.stdout, r.stdout[-2000:]
