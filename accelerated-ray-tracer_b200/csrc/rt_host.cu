@@ -106,6 +106,11 @@ void cached_free(void* p, size_t bytes, int dev) {
 
 template <class T> struct DBuf {
   T* p = nullptr; size_t n = 0; size_t bytes = 0; int dev = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), bytes(o.bytes), dev(o.dev) { o.p = nullptr; o.n = 0; o.bytes = 0; }
+  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; bytes = o.bytes; dev = o.dev; o.p = nullptr; o.n = 0; o.bytes = 0; } return *this; }
   cudaError_t alloc(size_t count) {
     free();
     n = count;
@@ -299,7 +304,6 @@ static int upload_scene(rt_scene* s) {
     texs[i] = d;
   }
   std::vector<DImage> images(sd.img.size());
-  s->image_px.reserve(sd.img.size());  // DBuf is not movable: no reallocation
   uint64_t bytes = 0;
   for (size_t i = 0; i < sd.img.size(); ++i) {
     const HostImage& im = sd.img_data[i];
