@@ -25,12 +25,7 @@ run $B --scene 7 --nx 600 --ny 600 --ns 1 --ids 1 --reps 0 --count 0 --textures 
 run $B --scene 8 --nx 600 --ny 600 --ns 1 --ids 1 --reps 0 --count 0 --textures $T --out $O/c3_600x600_ids
 run $B --scene 9 --nx 800 --ny 800 --ns 1 --ids 1 --reps 0 --count 0 --textures $T --out $O/c4_800x800_ids
 python tools/pack_goldens.py $O
-# converged images for the PSNR test (reference at high spp, reduced resolution: the reference runs at
-# 14-90 Mrays/s on B200)
-run $B --scene 7 --nx 200 --ny 200 --ns 2000 --reps 1 --count 0 --textures $T --out $O/c2_200x200_2000
-run $B --scene 8 --nx 200 --ny 200 --ns 2000 --reps 1 --count 0 --textures $T --out $O/c3_200x200_2000
-run $B --scene 9 --nx 200 --ny 200 --ns 1000 --reps 1 --count 0 --textures $T --out $O/c4_200x200_1000
-python tools/pack_goldens.py $O
+# converged images for the PSNR test: tools/gpu_ref_converged.sh (separate call: ~10 GPU-minutes)
 rm -f $O/*.sd $O/*.ids $O/*.fb
 cat $O/results.jsonl
 tail -5 $O/log.txt
