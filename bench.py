@@ -216,6 +216,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp-per-step", type=int, default=1000)
+    ap.add_argument("--split", default="spp", choices=["spp", "tile"],
+                    help="N > 1: spp split (default: every GPU renders all pixels for its own --spp-per-step samples, one NCCL "
+                         "reduce per step) or tile split (every GPU renders its interleaved scanlines for N x --spp-per-step "
+                         "samples, one NCCL gather per step); per-GPU work is the same in both")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -254,6 +258,12 @@ def main():
     spp_all = S * passes
 
     def step(i, profile=False):
+        if args.split == "tile" and world > 1:
+            # tile split: rank r owns scanlines j = r (mod N) and renders N x S samples for them; a different seed per step
+            st = sc.render(spp=S * world, rng_mode=0, split_mode=0, rank=rank, world=world, seed=1984 + i, profile=profile)
+            rdist.gather_rows_to_root(rdist.fb_tensor(sc).view(st.rows_local, st.nx, 3), NY)  # NCCL gather: the image on rank 0
+            torch.cuda.current_stream().synchronize()
+            return st
         st = sc.render(spp=spp_all, rng_mode=0, split_mode=1, rank=i * world + rank, world=passes, profile=profile)
         if world > 1:
             rdist.reduce_sum_to_root(rdist.accum_tensor(sc))  # NCCL reduce over NVLink: the image of this pass on rank 0
@@ -361,7 +371,7 @@ def main():
             "config": {"workload": "Book-2 final scene (create_world_final + earthmap) 800x800, depth 50, %d spp per step "
                                    "per GPU; default 10 steps = the 10000-spp config" % S,
                        "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": S, "spp_total": S * K * world,
-                       "max_depth": 50, "rng": "philox4x32-10", "parallelism": "spp-split x%d, scene replicated" % world,
+                       "max_depth": 50, "rng": "philox4x32-10", "parallelism": "%s-split x%d, scene replicated" % (args.split if world > 1 else "spp", world),
                        "l2": "inputs larger than L2: %.0f MB of path state (%d slots x 88 B) streamed every wave" %
                              (st.n_slots * 88 / 1e6, st.n_slots)},
             "msamples_per_s": round(samples_all / span_ms / 1e3, 3),
