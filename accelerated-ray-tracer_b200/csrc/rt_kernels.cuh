@@ -122,7 +122,9 @@ RT_D Ray start_sample(const DScene& S, const RenderParams& P, const PathArrays& 
 // Block-aggregated reservation: EVERY thread of the block calls it; threads with `pred` get consecutive
 // positions starting at a base taken with ONE global atomic per block (a wave of 1 Mi rays appends to a single
 // counter: one atomic per warp serialised 32 Ki same-address atomics in L2 and cost ~40% of k_shade, profiles/r01).
+#ifndef RT_BLOCK
 #define RT_BLOCK 256
+#endif
 #ifndef RT_SHADE_MINB
 #define RT_SHADE_MINB 3   // resident blocks per SM the shade kernel is compiled for (register cap 65536 / (256 * MINB))
 #endif
