@@ -402,21 +402,6 @@ static int upload_scene(rt_scene* s) {
   D.cam.u = v3(c.u[0], c.u[1], c.u[2]);
   D.cam.v = v3(c.v[0], c.v[1], c.v[2]);
   D.cam.lens_radius = c.lens_radius; D.cam.time0 = c.time0; D.cam.time1 = c.time1;
-  {  // hit-point cells of the shade-queue sub-bins: the two axes along which the object centroids spread most
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int k = 0; k < n; ++k)
-      for (int a = 0; a < 3; ++a) {
-        const float cc = 0.5f * boxes[k].mn[a] + 0.5f * boxes[k].mx[a];
-        lo[a] = std::min(lo[a], cc); hi[a] = std::max(hi[a], cc);
-      }
-    float ext[3]; for (int a = 0; a < 3; ++a) ext[a] = n > 0 ? hi[a] - lo[a] : 0.f;
-    int a0 = 0; for (int a = 1; a < 3; ++a) if (ext[a] > ext[a0]) a0 = a;
-    int a1 = (a0 + 1) % 3; { const int a2 = (a0 + 2) % 3; if (ext[a2] > ext[a1]) a1 = a2; }
-    D.cell_axis0 = a0; D.cell_axis1 = a1;
-    D.cell_lo0 = n > 0 ? lo[a0] : 0.f; D.cell_lo1 = n > 0 ? lo[a1] : 0.f;
-    D.cell_inv0 = ext[a0] > 0.f ? (float)RT_CELL_DIM / ext[a0] : 0.f;
-    D.cell_inv1 = ext[a1] > 0.f ? (float)RT_CELL_DIM / ext[a1] : 0.f;
-  }
   return 0;
 }
 
@@ -522,7 +507,7 @@ static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rn
   if (n_slots > s->slots_cap) {
     CU(s->ray_o.alloc(n_slots)); CU(s->ray_d.alloc(n_slots)); CU(s->thr.alloc(n_slots)); CU(s->rad.alloc(n_slots));
     CU(s->col.alloc(n_slots)); CU(s->hit.alloc(n_slots)); CU(s->order.alloc(n_slots + RT_MAX_POOLS * 32 * (Q_COUNT + 1)));
-    CU(s->queues.alloc(n_slots * RT_BINS));  // every bin can hold every slot; 180 GB of HBM make the fixed capacity cheap
+    CU(s->queues.alloc(n_slots * Q_COUNT));
     s->rng.free();
     s->slots_cap = n_slots;
   }
@@ -603,7 +588,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
       Ap[k] = A;
       Ap[k].ray_o += base; Ap[k].ray_d += base; Ap[k].hit += base; Ap[k].thr += base; Ap[k].rad += base; Ap[k].col += base;
       Ap[k].order += base + k * 32 * (Q_COUNT + 1);
-      queues_p[k] = s->queues.p + (size_t)RT_BINS * base;
+      queues_p[k] = s->queues.p + (size_t)Q_COUNT * base;
       base += n;
     }
   }
@@ -654,11 +639,10 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
           if (ref_rng) k_trace<RNG_REFERENCE><<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
           else k_trace<RNG_PHILOX><<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
           if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], sk));
-          k_layout<<<1, 128, 0, sk>>>(Ck, parity);
           if (ref_rng) k_shade<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
           else k_shade<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
           if (p->profile) CU(cudaEventRecord(pev[3 * w + 2], sk));
-          launches += 3;
+          launches += 2;
         }
         parity ^= 1; ++waves;
       }
@@ -673,7 +657,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
         if (done[k]) continue;
         CU(cudaEventSynchronize(evs[k]));
         int last = 0;
-        for (int q = 0; q < RT_BINS; ++q) last += s->h_counters[k].n_queue[parity ^ 1][q];
+        for (int q = 0; q < Q_COUNT; ++q) last += s->h_counters[k].n_queue[parity ^ 1][q];
         done[k] = last == 0;
         last_all += last;
       }

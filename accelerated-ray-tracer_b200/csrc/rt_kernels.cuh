@@ -41,8 +41,7 @@ struct PathArrays {
 };
 
 struct WaveCounters {
-  int n_queue[2][RT_BINS + 1]; // shade queue (bin) fill, by wave parity (their sum = rays traced in that wave)
-  int bin_off[RT_BINS + 1];    // k_layout: start of every bin in the shade / order layout (classes padded to whole warps)
+  int n_queue[2][Q_COUNT + 1]; // shade queue fill, by wave parity (their sum = rays traced in that wave)
   int order_len;               // entries of PathArrays::order in use
   unsigned long long rays;     // closest-hit queries issued (= the reference's bounce-loop iterations)
   unsigned long long samples;  // finished samples
@@ -196,8 +195,8 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, Re
                                                      WaveCounters* C, int parity) {
   __shared__ int s_cnt[RT_TWARPS];
   __shared__ unsigned long long s_wbase;
-  __shared__ int s_q[RT_TWARPS][RT_BINS];
-  __shared__ int s_qbase[RT_BINS];
+  __shared__ int s_q[RT_TWARPS][Q_COUNT];
+  __shared__ int s_qbase[Q_COUNT];
   // Thread -> slot through the previous wave's queue layout: paths that hit the same material class sit next to
   // each other, and the primary rays regenerated behind the miss / light queues come out in pixel order, which
   // keeps warps far more coherent than slot order (measured: 0.32 ms vs 0.53 ms per 1 Mi-ray wave on C4).
@@ -248,73 +247,53 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, Re
   }
   // ---- closest hit (main.cu:57) ----
   const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
-  int q = -1;  // shade-queue bin
+  int q = -1;
   if (active) {
     A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp < 0 ? -1 : (h.tlp | (h.face << 28))));
-    const int cls = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
-    int cell = 0;
-    if (RT_CELLS > 1 && cls >= 2) {
-      // spatial sub-bin of the hit point: the next wave walks the bins in order, so paths that continue from the same
-      // region of the scene sit in the same warps and start their traversal through the same subtree
-      const V3 hp = vmad(h.t, r.d, r.o);
-      const int c0 = min(max((int)((vget(hp, S.cell_axis0) - S.cell_lo0) * S.cell_inv0), 0), RT_CELL_DIM - 1);
-      const int c1 = min(max((int)((vget(hp, S.cell_axis1) - S.cell_lo1) * S.cell_inv1), 0), RT_CELL_DIM - 1);
-      cell = c1 * RT_CELL_DIM + c0;
-    }
-    q = bin_of(cls, cell);
+    q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
   }
-  // ---- binning: per-warp counts per bin in shared memory, ONE global atomic per non-empty bin per block ----
+  // ---- bin by material class: per-warp counts per class in shared memory, ONE global atomic per class per block ----
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int b = lane; b < RT_BINS; b += 32) s_q[warp][b] = 0;
+  if (lane < Q_COUNT) s_q[warp][lane] = 0;
   __syncwarp();
   const unsigned peers = __match_any_sync(0xFFFFFFFFu, q);
   if (q >= 0 && lane == __ffs(peers) - 1) s_q[warp][q] = __popc(peers);
   __syncthreads();
-  for (int b = threadIdx.x; b < RT_BINS; b += RT_TBLOCK) {
+  if (threadIdx.x < Q_COUNT) {
     int tot = 0;
 #pragma unroll
-    for (int w = 0; w < RT_TWARPS; ++w) { const int c = s_q[w][b]; s_q[w][b] = tot; tot += c; }
-    s_qbase[b] = tot > 0 ? atomicAdd(&C->n_queue[parity][b], tot) : 0;
+    for (int w = 0; w < RT_TWARPS; ++w) { const int c = s_q[w][threadIdx.x]; s_q[w][threadIdx.x] = tot; tot += c; }
+    s_qbase[threadIdx.x] = tot > 0 ? atomicAdd(&C->n_queue[parity][threadIdx.x], tot) : 0;
   }
   __syncthreads();
   if (q >= 0) queues[(size_t)q * P.n_slots + s_qbase[q] + s_q[warp][q] + __popc(peers & ((1u << lane) - 1u))] = slot;
 }
 
-// Layout of one wave's shade queues: bins laid end to end, each material class padded to a whole warp. One tiny block
-// between k_trace and k_shade; it also resets the other parity's counters for the next k_trace.
-__global__ void k_layout(WaveCounters* C, int parity) {
-  __shared__ int s_cnt[RT_BINS];
-  for (int b = threadIdx.x; b < RT_BINS; b += blockDim.x) { s_cnt[b] = C->n_queue[parity][b]; C->n_queue[parity ^ 1][b] = 0; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int off = 0, rays = 0;
-    for (int b = 0; b < RT_BINS; ++b) {
-      C->bin_off[b] = off;
-      off += s_cnt[b]; rays += s_cnt[b];
-      if (b + 1 == RT_BINS || class_of_bin(b + 1) != class_of_bin(b)) off = (off + 31) & ~31;
-    }
-    C->bin_off[RT_BINS] = off;
-    C->order_len = off;  // the next k_trace walks this layout
-    C->rays += (unsigned long long)rays;
-  }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, RenderParams P, PathArrays A, const int* __restrict__ queues,
                                                                    WaveCounters* C, int parity) {
-  // thread -> (bin, position) through k_layout's offsets; a warp never straddles two material classes
-  __shared__ int s_off[RT_BINS + 1];
-  for (int b = threadIdx.x; b <= RT_BINS; b += blockDim.x) s_off[b] = C->bin_off[b];
-  __syncthreads();
+  // thread -> (queue, position): queues are laid end to end, each padded to a whole warp
+  int cnt[Q_COUNT];
+  int total = 0, rays = 0;
+#pragma unroll
+  for (int k = 0; k < Q_COUNT; ++k) { cnt[k] = C->n_queue[parity][k]; total += (cnt[k] + 31) & ~31; rays += cnt[k]; }
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= s_off[RT_BINS]) return;
-  int lo = 0, hi = RT_BINS;  // largest bin with s_off[bin] <= gid
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= gid) lo = mid; else hi = mid; }
-  const int bin = lo;
-  const int q = class_of_bin(bin);
-  const int pos = gid - s_off[bin];
-  if (pos >= C->n_queue[parity][bin]) { A.order[gid] = -1; return; }  // warp padding behind a class
-  const int slot = queues[(size_t)bin * P.n_slots + pos];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < Q_COUNT; ++k) C->n_queue[parity ^ 1][k] = 0;  // next wave's trace fills these
+    C->rays += (unsigned long long)rays;
+    C->order_len = total;  // the next k_trace walks this wave's queue layout
+  }
+  if (gid >= total) return;
+  int q = 0, base = 0, qcount = cnt[0];
+#pragma unroll
+  for (int k = 0; k < Q_COUNT - 1; ++k) {
+    const int padded = (cnt[k] + 31) & ~31;
+    if (q == k && gid >= base + padded) { base += padded; q = k + 1; qcount = cnt[k + 1]; }
+  }
+  const int pos = gid - base;
+  if (pos >= qcount) { A.order[gid] = -1; return; }  // warp padding between two queues
+  const int slot = queues[(size_t)q * P.n_slots + pos];
   A.order[gid] = slot;
   const float4 o = A.ray_o[slot], d = A.ray_d[slot];
   const float4 thr4 = A.thr[slot], rad4 = A.rad[slot];

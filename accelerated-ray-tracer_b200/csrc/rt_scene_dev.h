@@ -63,10 +63,6 @@ struct DImage {
 // Shade-queue classes: what the trace kernel sorts paths by.
 // Q_PROCEDURAL: lambertian / isotropic whose texture chain evaluates Perlin noise (marble, noodle, felt): ~20x the
 // instructions of any other shade, so those paths get warps of their own.
-#ifndef RT_CELL_DIM
-#define RT_CELL_DIM 4   // RT_CELL_DIM^2 spatial sub-bins per continuing material class (1 = none)
-#endif
-#define RT_CELLS (RT_CELL_DIM * RT_CELL_DIM)
 enum QueueId : int { Q_MISS = 0, Q_LIGHT = 1, Q_LAMBERTIAN = 2, Q_METAL = 3, Q_DIELECTRIC = 4, Q_ISOTROPIC = 5, Q_PROCEDURAL = 6, Q_COUNT = 7 };
 
 struct alignas(16) DTlp {     // one per top-level object
@@ -99,14 +95,6 @@ struct DScene {
   const DTlp* tlp; const BVH4Node* nodes;
   int n_tlp, n_nodes;
   DCamera cam;
-  // hit-point cell of the shade-queue sub-bins (see k_trace): RT_CELL_DIM x RT_CELL_DIM cells over the two axes along
-  // which the objects' centroids spread most
-  int cell_axis0, cell_axis1; float cell_lo0, cell_lo1, cell_inv0, cell_inv1;
 };
-
-// Shade-queue bins: miss, light, then RT_CELLS spatial sub-bins for each continuing class.
-#define RT_BINS (2 + (Q_COUNT - 2) * RT_CELLS)
-RT_HD int bin_of(int q, int cell) { return q < 2 ? q : 2 + (q - 2) * RT_CELLS + cell; }
-RT_HD int class_of_bin(int b) { return b < 2 ? b : 2 + (b - 2) / RT_CELLS; }
 
 }  // namespace rt
