@@ -104,6 +104,13 @@ void cached_free(void* p, size_t bytes, int dev) {
 }
 }  // namespace
 
+// CUDA events that are destroyed on every exit path (the CU macro returns early on errors).
+struct Events {
+  std::vector<cudaEvent_t> v;
+  cudaError_t make(cudaEvent_t* e, unsigned flags = cudaEventDefault) { cudaError_t r = cudaEventCreateWithFlags(e, flags); if (r == cudaSuccess) v.push_back(*e); return r; }
+  ~Events() { for (auto e : v) cudaEventDestroy(e); }
+};
+
 template <class T> struct DBuf {
   T* p = nullptr; size_t n = 0; size_t bytes = 0; int dev = 0;
   DBuf() = default;
@@ -330,7 +337,8 @@ static int upload_scene(rt_scene* s) {
   CU(s->nodes.alloc(std::max(n, 1)));
   DBuf<int> d_nout; CU(d_nout.alloc(1));
   cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  Events evh;
+  CU(evh.make(&e0)); CU(evh.make(&e1));
   CU(cudaEventRecord(e0));
   if (n <= 1) {
     k_bvh_trivial<<<1, 1>>>(n, d_boxes.p, d_refs.p, s->nodes.p, d_nout.p);
@@ -386,7 +394,6 @@ static int upload_scene(rt_scene* s) {
   CU(cudaEventSynchronize(e1));
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&s->bvh_ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   CU(cudaMemcpy(&s->n_nodes, d_nout.p, sizeof(int), cudaMemcpyDeviceToHost));
   s->h2d_bytes = bytes;
 
@@ -572,8 +579,9 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   cudaStream_t st = s->stream;
   cudaStream_t* streams = s->pool_stream;
   cudaEvent_t e0, e1, evs[RT_MAX_POOLS];
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  for (int k = 0; k < RT_MAX_POOLS; ++k) CU(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+  Events evh;
+  CU(evh.make(&e0)); CU(evh.make(&e1));
+  for (int k = 0; k < RT_MAX_POOLS; ++k) CU(evh.make(&evs[k], cudaEventDisableTiming));
   CU(cudaEventRecord(e0, st));
   // pool geometry: pool k owns a contiguous range of the slots and the same ranges of the queues / order arrays
   RenderParams Pp[RT_MAX_POOLS];
@@ -610,12 +618,11 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     FILE* wlog = nullptr;  // diagnostics: one line per wave (rays of the wave, k_trace ms, k_shade ms)
     if (p->profile) if (const char* e = getenv("RT_WAVE_LOG")) { wlog = fopen(e, "a"); batch = 1; }
     std::vector<cudaEvent_t> pev;
-    if (p->profile) { pev.resize(3 * batch); for (auto& e : pev) CU(cudaEventCreate(&e)); }
+    if (p->profile) { pev.resize(3 * batch); for (auto& e : pev) CU(evh.make(&e)); }
     cudaEvent_t eset;
-    CU(cudaEventCreateWithFlags(&eset, cudaEventDisableTiming));
+    CU(evh.make(&eset, cudaEventDisableTiming));
     CU(cudaEventRecord(eset, st));
     for (int k = 1; k < n_pools; ++k) CU(cudaStreamWaitEvent(streams[k], eset, 0));  // the other pools start after the counters are set
-    cudaEventDestroy(eset);
     int G[RT_MAX_POOLS], Gs[RT_MAX_POOLS], Gt[RT_MAX_POOLS];
     for (int k = 0; k < n_pools; ++k) {
       G[k] = (Pp[k].n_slots + B - 1) / B;
@@ -671,7 +678,6 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
         }
       }
     }
-    for (auto& e : pev) cudaEventDestroy(e);
     if (wlog) fclose(wlog);
     for (int k = 1; k < n_pools; ++k) {  // pool 0's stream carries on alone: it waits for the other pools' last kernels
       CU(cudaEventRecord(evs[k], streams[k]));
@@ -698,8 +704,6 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  for (int k = 0; k < RT_MAX_POOLS; ++k) cudaEventDestroy(evs[k]);
   unsigned long long rays_all = 0; unsigned int overflow_all = 0, nonfinite_all = 0;
   for (int k = 0; k < RT_MAX_POOLS; ++k) { rays_all += s->h_counters[k].rays; overflow_all |= s->h_counters[k].overflow; nonfinite_all += s->h_counters[k].nonfinite; }
   s->last = P; s->has_aov = p->aov != 0; s->last_gamma = gamma; s->last_spp_total = spp_total;
