@@ -50,6 +50,9 @@ def texture_dir():
     raise SystemExit("bench: earthmap.ppm not found (run __graft_entry__.build() where /root/reference exists)")
 
 
+NCU_EXTRA = {}
+
+
 def ncu_traffic_per_ray(kernel="k_trace<0>"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the latest committed ncu capture (profiles/*_traffic.json,
     written by tools/summarize_profile.py), per ray of that launch (grid x block threads, one ray each)."""
@@ -60,6 +63,7 @@ def ncu_traffic_per_ray(kernel="k_trace<0>"):
     d = json.load(open(files[-1])).get(kernel)
     if not d:
         return None, None
+    NCU_EXTRA.update({k: d.get(k) for k in ("inst_issued_pct_of_peak", "threads_per_instruction", "l1_hit_pct", "l2_hit_pct", "fma_pipe_pct")})
     return d["dram_bytes"] / (d["grid"] * d["block"]), os.path.basename(files[-1])
 
 
@@ -385,6 +389,8 @@ def main():
                          "traffic": round(tpr * rays_per_launch) if tpr else None,
                          "traffic_source": ("ncu dram bytes/ray of %s x rays per launch" % tsrc) if tpr else None,
                          "peak_source": peak_src,
+                         "binding_resource": {"what": "instruction issue (not HBM, not FP32 lanes): ncu metrics of the same kernel from "
+                                                      "the committed capture", **NCU_EXTRA} if NCU_EXTRA else None,
                          "algorithmic_bytes_per_ray": C4_TRACE_BYTES_PER_RAY,
                          "rays_per_launch": round(rays_per_launch, 1), "launch_ms": round(trace_ms / n_launch, 5),
                          "share_of_kernel_time": {"k_trace": round(trace_ms / max(trace_ms + shade_ms, 1e-9), 4),

@@ -71,7 +71,11 @@ if os.path.exists(rep):
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         traffic[n] = {"dram_bytes": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
                       "grid": int(num(r[hdr.index("launch__grid_size")])), "block": int(num(r[hdr.index("launch__block_size")])),
-                      "duration_us": num(r[hdr.index("gpu__time_duration.sum")]) / (1000.0 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1.0)}
+                      "duration_us": num(r[hdr.index("gpu__time_duration.sum")]) / (1000.0 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1.0),
+                      "inst_issued_pct_of_peak": num(r[hdr.index("sm__inst_issued.avg.pct_of_peak_sustained_active")]) if "sm__inst_issued.avg.pct_of_peak_sustained_active" in hdr else None,
+                      "threads_per_instruction": num(r[hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")]),
+                      "l1_hit_pct": num(r[hdr.index("l1tex__t_sector_hit_rate.pct")]), "l2_hit_pct": num(r[hdr.index("lts__t_sector_hit_rate.pct")]),
+                      "fma_pipe_pct": num(r[hdr.index("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")])}
     json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
     # ---- per-source-line attribution ----
     sass = os.path.join(G, "elf", "all_%s.sass" % tag)
