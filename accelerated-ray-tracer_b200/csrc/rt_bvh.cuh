@@ -194,7 +194,7 @@ struct PlocAlive { __device__ bool operator()(int v) const { return v >= 0; } };
 // Collapse to 4-wide nodes. One CTA, level-synchronous work queue: task = (binary node, output node).
 // Each task opens the interior child with the largest surface area until it has 4 children.
 __global__ void __launch_bounds__(1024) k_bvh_collapse(int n, int root, const int* left, const int* right, const BuildBox* nbox,
-                                                       const int* sorted, const uint32_t* tlp_ref, BVH4Node* out,
+                                                       const int* sorted, const DTlp* tlps, BVH4Node* out,
                                                        int* n_out, int2* qa, int2* qb) {
   __shared__ int s_count, s_next;
   if (threadIdx.x == 0) { qa[0] = make_int2(root, 0); s_count = 1; s_next = 0; *n_out = 1; }
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(1024) k_bvh_collapse(int n, int root, const in
           node.hix[c] = b.mx[0]; node.hiy[c] = b.mx[1]; node.hiz[c] = b.mx[2];
           if (kids[c] >= n - 1) {
             const int obj = sorted[kids[c] - (n - 1)];
-            node.child[c] = tlp_ref[obj]; node.tlp[c] = (uint32_t)obj;
+            node.child[c] = tlps[obj].ref; node.tlp[c] = (uint32_t)obj | ((uint32_t)tlps[obj].queue << 28);
           } else {
             const int o = o_next++;
             node.child[c] = RT_NODE_FLAG | (uint32_t)o; node.tlp[c] = 0;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(1024) k_bvh_collapse(int n, int root, const in
 }
 
 // n == 1 (and n == 0): a root with one (no) leaf child.
-__global__ void k_bvh_trivial(int n, const BuildBox* boxes, const uint32_t* tlp_ref, BVH4Node* out, int* n_out) {
+__global__ void k_bvh_trivial(int n, const BuildBox* boxes, const DTlp* tlps, BVH4Node* out, int* n_out) {
   BVH4Node node;
   for (int c = 0; c < 4; ++c) {
     node.lox[c] = node.loy[c] = node.loz[c] = FLT_MAX;
@@ -260,7 +260,7 @@ __global__ void k_bvh_trivial(int n, const BuildBox* boxes, const uint32_t* tlp_
   if (n == 1) {
     node.lox[0] = boxes[0].mn[0]; node.loy[0] = boxes[0].mn[1]; node.loz[0] = boxes[0].mn[2];
     node.hix[0] = boxes[0].mx[0]; node.hiy[0] = boxes[0].mx[1]; node.hiz[0] = boxes[0].mx[2];
-    node.child[0] = tlp_ref[0]; node.tlp[0] = 0;
+    node.child[0] = tlps[0].ref; node.tlp[0] = (uint32_t)tlps[0].queue << 28;
   }
   out[0] = node;
   *n_out = 1;

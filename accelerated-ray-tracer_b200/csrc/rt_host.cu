@@ -67,8 +67,17 @@ struct HostDevMath : DevMath {  // rt_scene_export_host only
 namespace {
 std::mutex g_cache_mu;
 std::map<std::pair<int, size_t>, std::vector<void*>> g_cache;  // (device, bytes) -> free blocks
-size_t g_cache_bytes = 0;
-const size_t kCacheMaxTotal = (size_t)16 << 30;
+std::map<int, size_t> g_cache_bytes;  // per device
+size_t cache_cap_bytes() {  // per-device cap of the free list (RT_CACHE_MAX_MB overrides the 8 GiB default)
+  static const size_t cap = [] { const char* e = getenv("RT_CACHE_MAX_MB"); return e ? (size_t)atoll(e) << 20 : (size_t)8 << 30; }();
+  return cap;
+}
+void trim_device_locked(int dev) {  // caller holds g_cache_mu and has made `dev` current
+  for (auto it = g_cache.begin(); it != g_cache.end();) {
+    if (it->first.first == dev) { for (void* p : it->second) cudaFree(p); it = g_cache.erase(it); } else ++it;
+  }
+  g_cache_bytes[dev] = 0;
+}
 
 size_t canonical_bytes(size_t want) {  // sizes are rounded so that a slightly different scene finds the same block sizes
   if (want < 512) return 512;
@@ -84,19 +93,25 @@ cudaError_t cached_malloc(void** out, size_t bytes) {
     if (it != g_cache.end() && !it->second.empty()) {
       *out = it->second.back();
       it->second.pop_back();
-      g_cache_bytes -= bytes;
+      g_cache_bytes[dev] -= bytes;
       return cudaSuccess;
     }
   }
-  return cudaMalloc(out, bytes);
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // the memory may be sitting in our own free list under other size classes
+    cudaGetLastError();
+    { std::lock_guard<std::mutex> lk(g_cache_mu); trim_device_locked(dev); }
+    e = cudaMalloc(out, bytes);
+  }
+  return e;
 }
 void cached_free(void* p, size_t bytes, int dev) {
   if (!p) return;
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    if (g_cache_bytes + bytes <= kCacheMaxTotal) {
+    if (g_cache_bytes[dev] + bytes <= cache_cap_bytes()) {
       g_cache[std::make_pair(dev, bytes)].push_back(p);
-      g_cache_bytes += bytes;
+      g_cache_bytes[dev] += bytes;
       return;
     }
   }
@@ -118,12 +133,15 @@ template <class T> struct DBuf {
   DBuf& operator=(const DBuf&) = delete;
   DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), bytes(o.bytes), dev(o.dev) { o.p = nullptr; o.n = 0; o.bytes = 0; }
   DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; bytes = o.bytes; dev = o.dev; o.p = nullptr; o.n = 0; o.bytes = 0; } return *this; }
-  cudaError_t alloc(size_t count) {
+  cudaError_t alloc(size_t count) {  // n / bytes are committed only when the allocation succeeded
     free();
-    n = count;
-    bytes = canonical_bytes(std::max<size_t>(count, 1) * sizeof(T));
+    const size_t want = canonical_bytes(std::max<size_t>(count, 1) * sizeof(T));
     cudaGetDevice(&dev);
-    return cached_malloc((void**)&p, bytes);
+    void* q = nullptr;
+    const cudaError_t e = cached_malloc(&q, want);
+    if (e != cudaSuccess) return e;
+    p = (T*)q; n = count; bytes = want;
+    return cudaSuccess;
   }
   cudaError_t upload(const std::vector<T>& h) {
     cudaError_t e = alloc(h.size());
@@ -155,15 +173,18 @@ void ctx_release(const HostCtx& c) { std::lock_guard<std::mutex> lk(g_cache_mu);
 
 extern "C" void rt_trim_device_cache(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
+  int cur = -1;
+  cudaGetDevice(&cur);  // restored below: the caller's current device is not ours to change
   for (auto& kv : g_cache) { cudaSetDevice(kv.first.first); for (void* p : kv.second) cudaFree(p); }
   g_cache.clear();
-  g_cache_bytes = 0;
+  g_cache_bytes.clear();
   for (auto& c : g_ctx_pool) {
     cudaSetDevice(c.dev);
     for (int k = 0; k < RT_MAX_POOLS; ++k) if (c.streams[k]) cudaStreamDestroy(c.streams[k]);
     if (c.pinned) cudaFreeHost(c.pinned);
   }
   g_ctx_pool.clear();
+  if (cur >= 0) cudaSetDevice(cur);
 }
 
 struct rt_scene {
@@ -172,15 +193,15 @@ struct rt_scene {
   std::vector<int> rank;
   // flattened scene
   DBuf<DSphere> spheres; DBuf<DQuad> quads; DBuf<DXform> xforms; DBuf<DMedium> media;
-  DBuf<DMat> mats; DBuf<DTex> texs; DBuf<DImage> images; DBuf<DTlp> tlp; DBuf<BVH4Node> nodes;
+  DBuf<DMat> mats; DBuf<DTex> texs; DBuf<DImage> images; DBuf<DTlp> tlp; DBuf<BVH4Node> nodes; DBuf<float4> qplanes;
   std::vector<DBuf<unsigned char>> image_px;
   HostCtx ctx; bool has_ctx = false;
   DScene dscene;
   int n_nodes = 0; float bvh_ms = 0.f; uint64_t h2d_bytes = 0;
   // render state
   cudaStream_t stream = nullptr, pool_stream[RT_MAX_POOLS] = {nullptr};  // pool 0 runs on `stream`
-  DBuf<float4> ray_o, ray_d, thr, rad, col; DBuf<float2> hit; DBuf<uint32_t> rng;
-  DBuf<int> queues, order;
+  DBuf<float4> ray_o[2], ray_d[2], thr[2], rad[2], col; DBuf<float2> hit; DBuf<uint32_t> rng;
+  DBuf<int> queues;
   DBuf<WaveCounters> counters;          // one per slot pool
   DBuf<unsigned long long> next_work;
   WaveCounters* h_counters = nullptr;  // pinned, one per slot pool
@@ -188,6 +209,9 @@ struct rt_scene {
   size_t slots_cap = 0, pix_cap = 0, accum_valid_pix = 0;
   RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
   ~rt_scene() {
+    // kernels of a failed rt_render may still be in flight on the pool streams: nothing goes back to the block cache
+    // (where the next scene could pick it up) before the device is idle
+    cudaDeviceSynchronize();
     if (has_ctx) ctx_release(ctx);
   }
 };
@@ -325,6 +349,11 @@ static int upload_scene(rt_scene* s) {
     images[i].data = d; images[i].width = im.width; images[i].height = im.height; images[i].bpp = im.bpp; images[i].pad = 0;
     bytes += im.px.size();
   }
+  {
+    std::vector<float4> qp(F.quads.size());
+    for (size_t i = 0; i < qp.size(); ++i) qp[i] = make_float4(F.quads[i].nx, F.quads[i].ny, F.quads[i].nz, F.quads[i].D);
+    CU(s->qplanes.upload(qp));
+  }
   CU(s->spheres.upload(F.spheres)); CU(s->quads.upload(F.quads)); CU(s->xforms.upload(F.xforms)); CU(s->media.upload(F.media));
   CU(s->mats.upload(mats)); CU(s->texs.upload(texs)); CU(s->images.upload(images)); CU(s->tlp.upload(tlp));
   bytes += F.spheres.size() * sizeof(DSphere) + F.quads.size() * sizeof(DQuad) + F.xforms.size() * sizeof(DXform) +
@@ -341,7 +370,7 @@ static int upload_scene(rt_scene* s) {
   CU(evh.make(&e0)); CU(evh.make(&e1));
   CU(cudaEventRecord(e0));
   if (n <= 1) {
-    k_bvh_trivial<<<1, 1>>>(n, d_boxes.p, d_refs.p, s->nodes.p, d_nout.p);
+    k_bvh_trivial<<<1, 1>>>(n, d_boxes.p, s->tlp.p, s->nodes.p, d_nout.p);
   } else {
     const int B = 256, G = (n + B - 1) / B;
     DBuf<unsigned int> cb; CU(cb.alloc(6));
@@ -386,7 +415,7 @@ static int upload_scene(rt_scene* s) {
     }
     CU(cudaMemcpy(&root, cl_a.p, sizeof(int), cudaMemcpyDeviceToHost));
 #endif
-    k_bvh_collapse<<<1, 1024>>>(n, root, left.p, right.p, nbox.p, v_out.p, d_refs.p, s->nodes.p, d_nout.p, qa.p, qb.p);
+    k_bvh_collapse<<<1, 1024>>>(n, root, left.p, right.p, nbox.p, v_out.p, s->tlp.p, s->nodes.p, d_nout.p, qa.p, qb.p);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
   }
@@ -399,7 +428,7 @@ static int upload_scene(rt_scene* s) {
 
   DScene& D = s->dscene;
   D.spheres = s->spheres.p; D.quads = s->quads.p; D.xforms = s->xforms.p; D.media = s->media.p;
-  D.mats = s->mats.p; D.texs = s->texs.p; D.images = s->images.p; D.tlp = s->tlp.p; D.nodes = s->nodes.p;
+  D.mats = s->mats.p; D.texs = s->texs.p; D.images = s->images.p; D.tlp = s->tlp.p; D.nodes = s->nodes.p; D.qplanes = s->qplanes.p;
   D.n_tlp = n; D.n_nodes = s->n_nodes;
   const rt_camera_desc& c = sd.cam;
   D.cam.origin = v3(c.origin[0], c.origin[1], c.origin[2]);
@@ -510,20 +539,28 @@ extern "C" int rt_scene_export_host(const rt_scene_desc* desc, void* buf, size_t
   return export_sd(sd, rk, buf, cap, needed, rank, rank_cap);
 }
 
+// Capacity of a pool's dense layout: its paths plus the warp padding between the RT_NQ queues, in whole trace ranges.
+static size_t pool_cap(size_t n) { return (n + 32 * RT_NQ + RT_RANGE - 1) / RT_RANGE * RT_RANGE; }
+static size_t pool_subcap(size_t n) { return ((pool_cap(n) / RT_RANGE + RT_NSUB - 1) / RT_NSUB + 1) * RT_RANGE; }
+
 static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rng, bool aov) {
   if (n_slots > s->slots_cap) {
-    CU(s->ray_o.alloc(n_slots)); CU(s->ray_d.alloc(n_slots)); CU(s->thr.alloc(n_slots)); CU(s->rad.alloc(n_slots));
-    CU(s->col.alloc(n_slots)); CU(s->hit.alloc(n_slots)); CU(s->order.alloc(n_slots + RT_MAX_POOLS * 32 * (Q_COUNT + 1)));
-    CU(s->queues.alloc(n_slots * Q_COUNT));
+    s->slots_cap = 0;  // a failure below must not leave a capacity that the freed / null buffers do not back
     s->rng.free();
+    // worst case over the pool counts: RT_MAX_POOLS pools, each with its own padding
+    const size_t cap = pool_cap(n_slots) + RT_MAX_POOLS * pool_cap(0);
+    for (int k = 0; k < 2; ++k) { CU(s->ray_o[k].alloc(cap)); CU(s->ray_d[k].alloc(cap)); CU(s->thr[k].alloc(cap)); CU(s->rad[k].alloc(cap)); }
+    CU(s->hit.alloc(cap));
+    CU(s->queues.alloc((size_t)RT_NQ * (pool_subcap(n_slots) + RT_MAX_POOLS * pool_subcap(0))));
     s->slots_cap = n_slots;
   }
-  if (ref_rng && s->rng.n < 6 * n_slots) CU(s->rng.alloc(6 * s->slots_cap));
   if (n_pix > s->pix_cap) {
-    CU(s->accum.alloc(3 * n_pix)); CU(s->fb.alloc(3 * n_pix)); CU(s->acc64.alloc(3 * n_pix));
-    s->aov_obj.free(); s->aov_mat.free(); s->aov_t.free();
-    s->pix_cap = n_pix; s->accum_valid_pix = 0;
+    s->pix_cap = 0; s->accum_valid_pix = 0;
+    s->aov_obj.free(); s->aov_mat.free(); s->aov_t.free(); s->rng.free();
+    CU(s->accum.alloc(3 * n_pix)); CU(s->fb.alloc(3 * n_pix)); CU(s->acc64.alloc(3 * n_pix)); CU(s->col.alloc(n_pix));
+    s->pix_cap = n_pix;
   }
+  if (ref_rng && s->rng.n < 6 * n_pix) CU(s->rng.alloc(6 * s->pix_cap));
   if (aov && s->aov_obj.n < n_pix) { CU(s->aov_obj.alloc(s->pix_cap)); CU(s->aov_mat.alloc(s->pix_cap)); CU(s->aov_t.alloc(s->pix_cap)); }
   if (!s->counters.p) { CU(s->counters.alloc(RT_MAX_POOLS)); CU(s->next_work.alloc(1)); }
   return 0;
@@ -554,7 +591,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   if (ref_rng) {
     P.n_slots = (int)n_pix;  // a slot is a pixel: one sequential XORWOW stream each
   } else {
-    long long target = p->slots > 0 ? p->slots : 2 * 1024 * 1024;  // sweep on C4: 1 Mi .. 4 Mi within 2%, 512 Ki -8%
+    long long target = p->slots > 0 ? p->slots : 8 * 1024 * 1024;  // sweep on C4 (4 pools): 2 Mi 3737, 8 Mi 3825 Mrays/s: longer kernels, smaller tails
     if (p->slots <= 0) if (const char* e = getenv("RT_SLOTS")) target = atoll(e);
     target = (target + 127) / 128 * 128;
     P.n_slots = (int)std::max<long long>(0, std::min<long long>(target, P.work_total));
@@ -567,15 +604,16 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   const float gamma = p->gamma > 0 ? p->gamma : 2.2f;
   if (ensure_buffers(s, std::max(P.n_slots, 1), n_pix, ref_rng, p->aov != 0)) return 1;
 
-  // Slot pools: the slots are split into independent halves, each running its own trace -> shade chain on its own
-  // stream. k_trace is issue-bound and k_shade latency-bound, so letting one pool's shade run under the other
+  // Path pools: the paths are split into independent pools, each running its own trace -> shade chain on its own
+  // stream. k_trace is issue-bound and k_shade latency-bound, so letting one pool's shade run under another
   // pool's trace fills issue slots that a single chain leaves idle. The pools share only the work counter and the
   // fixed-point accumulators (atomics). Reference-RNG mode and per-kernel profiling use one pool.
-  int n_pools = (ref_rng || p->profile) ? 1 : P.n_slots >= 1024 * 1024 ? 4 : P.n_slots >= 256 * 1024 ? 2 : 1;  // C4: 1 pool 2480, 2 pools 2810, 4 pools 2870 Mrays/s
-  if (const char* e = getenv("RT_POOLS")) n_pools = (!ref_rng && P.n_slots >= RT_MAX_POOLS * RT_BLOCK) ? std::max(1, std::min(RT_MAX_POOLS, atoi(e))) : 1;
+  int n_pools = (ref_rng || p->profile) ? 1 : P.n_slots >= 1024 * 1024 ? 4 : P.n_slots >= 256 * 1024 ? 2 : 1;
+  if (const char* e = getenv("RT_POOLS")) if (!ref_rng && !p->profile) n_pools = std::max(1, std::min(RT_MAX_POOLS, atoi(e)));
+  n_pools = std::max(1, std::min(n_pools, P.n_slots / (4 * RT_BLOCK)));  // every pool gets at least a few blocks of paths
   PathArrays A;
-  A.ray_o = s->ray_o.p; A.ray_d = s->ray_d.p; A.hit = s->hit.p; A.thr = s->thr.p; A.rad = s->rad.p; A.col = s->col.p;
-  A.rng = s->rng.p; A.acc64 = s->acc64.p; A.order = s->order.p; A.next_work = s->next_work.p;
+  memset(&A, 0, sizeof(A));
+  A.col = s->col.p; A.rng = s->rng.p; A.acc64 = s->acc64.p; A.next_work = s->next_work.p;
   cudaStream_t st = s->stream;
   cudaStream_t* streams = s->pool_stream;
   cudaEvent_t e0, e1, evs[RT_MAX_POOLS];
@@ -583,36 +621,41 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   CU(evh.make(&e0)); CU(evh.make(&e1));
   for (int k = 0; k < RT_MAX_POOLS; ++k) CU(evh.make(&evs[k], cudaEventDisableTiming));
   CU(cudaEventRecord(e0, st));
-  // pool geometry: pool k owns a contiguous range of the slots and the same ranges of the queues / order arrays
+  // pool geometry: pool k owns a contiguous range of every path array and of the queue storage
   RenderParams Pp[RT_MAX_POOLS];
   PathArrays Ap[RT_MAX_POOLS];
-  int* queues_p[RT_MAX_POOLS];
+  size_t capk[RT_MAX_POOLS] = {0};
   {
     const int per = (P.n_slots / n_pools + RT_BLOCK - 1) / RT_BLOCK * RT_BLOCK;
-    int base = 0;
+    int base = 0; size_t abase = 0, qbase = 0;
     for (int k = 0; k < n_pools; ++k) {
       const int n = (k == n_pools - 1) ? P.n_slots - base : std::min(per, P.n_slots - base);
       Pp[k] = P; Pp[k].n_slots = n;
       Ap[k] = A;
-      Ap[k].ray_o += base; Ap[k].ray_d += base; Ap[k].hit += base; Ap[k].thr += base; Ap[k].rad += base; Ap[k].col += base;
-      Ap[k].order += base + k * 32 * (Q_COUNT + 1);
-      queues_p[k] = s->queues.p + (size_t)Q_COUNT * base;
+      for (int b = 0; b < 2; ++b) { Ap[k].ray_o[b] = s->ray_o[b].p + abase; Ap[k].ray_d[b] = s->ray_d[b].p + abase; Ap[k].thr[b] = s->thr[b].p + abase; Ap[k].rad[b] = s->rad[b].p + abase; }
+      Ap[k].hit = s->hit.p + abase;
+      Ap[k].queues = s->queues.p + qbase;
+      Ap[k].subcap = (int)pool_subcap(n);
+      capk[k] = pool_cap(n);
+      abase += capk[k]; qbase += (size_t)RT_NQ * pool_subcap(n);
       base += n;
     }
   }
   {
     for (int k = 0; k < RT_MAX_POOLS; ++k) { memset(&s->h_counters[k], 0, sizeof(WaveCounters)); if (k < n_pools) s->h_counters[k].order_len = Pp[k].n_slots; }
     CU(cudaMemcpyAsync(s->counters.p, s->h_counters, RT_MAX_POOLS * sizeof(WaveCounters), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(s->next_work.p, 0, sizeof(unsigned long long), st));
+    // the first n_slots work items are drawn by k_init; reference-RNG mode does not use the counter
+    const unsigned long long first_work = (unsigned long long)P.n_slots;
+    CU(cudaMemcpyAsync(s->next_work.p, &first_work, sizeof(first_work), cudaMemcpyHostToDevice, st));
     if (!ref_rng && n_pix > 0) CU(cudaMemsetAsync(s->acc64.p, 0, 3 * n_pix * sizeof(unsigned long long), st));
   }
   const int B = RT_BLOCK;
   int launches = 0, waves = 0, prof_waves = 0;
   double prof_trace_ms = 0.0, prof_shade_ms = 0.0;
   if (P.n_slots > 0 && P.sample_count > 0) {
-    // Every wave of a pool runs k_trace over its slots (a slot whose sample ended regenerates there) and k_shade over
-    // the queues that wave filled. The host reads the queue fills back every `batch` waves: a wave that traced no
-    // ray means every slot of the pool is dead; the job is done when both pools are.
+    // Every wave of a pool runs k_trace over its dense layout and k_shade over the queues that wave filled (a lane
+    // whose sample ended takes the next work item there). The host reads the queue fills back every `batch` waves: a
+    // wave that traced no ray means the pool has run out of work; the job is done when all pools have.
     int batch = 8;
     if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
     FILE* wlog = nullptr;  // diagnostics: one line per wave (rays of the wave, k_trace ms, k_shade ms)
@@ -623,14 +666,18 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     CU(evh.make(&eset, cudaEventDisableTiming));
     CU(cudaEventRecord(eset, st));
     for (int k = 1; k < n_pools; ++k) CU(cudaStreamWaitEvent(streams[k], eset, 0));  // the other pools start after the counters are set
-    int G[RT_MAX_POOLS], Gs[RT_MAX_POOLS], Gt[RT_MAX_POOLS];
-    for (int k = 0; k < n_pools; ++k) {
-      G[k] = (Pp[k].n_slots + B - 1) / B;
-      Gs[k] = (Pp[k].n_slots + 32 * Q_COUNT + B - 1) / B;
-      Gt[k] = (Pp[k].n_slots + 32 * Q_COUNT + RT_TBLOCK - 1) / RT_TBLOCK;
-      if (ref_rng) k_init<RNG_REFERENCE><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
-      else k_init<RNG_PHILOX><<<G[k], B, 0, streams[k]>>>(Pp[k], Ap[k]);
-      ++launches;
+    int Gs[RT_MAX_POOLS], Gt[RT_MAX_POOLS];
+    {
+      int work_base = 0;  // pool k draws work items [work_base, work_base + n_k) in k_init
+      for (int k = 0; k < n_pools; ++k) {
+        const int G = (Pp[k].n_slots + B - 1) / B;
+        Gs[k] = (int)((capk[k] + B - 1) / B);
+        Gt[k] = (int)((capk[k] / RT_RANGE + RT_TWARPS - 1) / RT_TWARPS);
+        if (ref_rng) k_init<RNG_REFERENCE><<<G, B, 0, streams[k]>>>(s->dscene, Pp[k], Ap[k], work_base);
+        else k_init<RNG_PHILOX><<<G, B, 0, streams[k]>>>(s->dscene, Pp[k], Ap[k], work_base);
+        work_base += Pp[k].n_slots;
+        ++launches;
+      }
     }
     int parity = 0;
     bool done[RT_MAX_POOLS];
@@ -643,11 +690,11 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
           cudaStream_t sk = streams[k];
           WaveCounters* Ck = s->counters.p + k;
           if (p->profile) CU(cudaEventRecord(pev[3 * w], sk));
-          if (ref_rng) k_trace<RNG_REFERENCE><<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
-          else k_trace<RNG_PHILOX><<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          k_trace<<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, P.tmin, Ap[k].ray_o[parity], Ap[k].ray_d[parity], Ap[k].hit, Ap[k].queues,
+                                               Ap[k].subcap, Ck, parity);
           if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], sk));
-          if (ref_rng) k_shade<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
-          else k_shade<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], queues_p[k], Ck, parity);
+          if (ref_rng) k_shade<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], Ck, parity);
+          else k_shade<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], Ck, parity);
           if (p->profile) CU(cudaEventRecord(pev[3 * w + 2], sk));
           launches += 2;
         }
@@ -664,7 +711,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
         if (done[k]) continue;
         CU(cudaEventSynchronize(evs[k]));
         int last = 0;
-        for (int q = 0; q < Q_COUNT; ++q) last += s->h_counters[k].n_queue[parity ^ 1][q];
+        for (int q = 0; q < RT_NQ; ++q) last += s->h_counters[k].n_queue[parity ^ 1][q];
         done[k] = last == 0;
         last_all += last;
       }

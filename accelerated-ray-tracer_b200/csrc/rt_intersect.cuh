@@ -93,13 +93,13 @@ RT_D void quad_fill(const DQuad& q, const Ray& r, float t, float alpha, float be
 // test passes, the LATER face on an exact tie (the interval test is inclusive). Computed here as: six plane
 // distances first (independent loads), then interior tests in ascending-t order until one passes - usually one
 // interior test instead of six.
-RT_D bool box_hit(const DQuad* faces, const Ray& r, float tmin, float tmax, float& t_out, int& face, float& alpha,
+RT_D bool box_hit(const DQuad* faces, const float4* planes, const Ray& r, float tmin, float tmax, float& t_out, int& face, float& alpha,
                   float& beta) {
   float tf[6];
   unsigned valid = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    const float4 nD = __ldg(reinterpret_cast<const float4*>(faces + i));
+    const float4 nD = __ldg(planes + i);  // the six (normal, D) of a box are contiguous: 96 B instead of six 80-B strides
     tf[i] = FLT_MAX;
     if (quad_plane(nD, r, tmin, tmax, tf[i])) valid |= 1u << i;
   }
@@ -159,7 +159,7 @@ RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax,
     if (FULL && known_face >= 0) {
       face = known_face;
       if (!quad_hit(S.quads[ix + face], r, tmin, tmax, t, a, b)) return false;
-    } else if (!box_hit(S.quads + ix, r, tmin, tmax, t, face, a, b)) return false;
+    } else if (!box_hit(S.quads + ix, S.qplanes + ix, r, tmin, tmax, t, face, a, b)) return false;
     rec.t = t; rec.face = face;
     if (FULL) quad_fill(S.quads[ix + face], r, t, a, b, rec);
   } else {
@@ -256,6 +256,12 @@ __device__ unsigned long long g_stats2[4];  // per node phase: lanes finished, l
 #define RT_COUNT(i, n) do { } while (0)
 #endif
 
+// The tlp word of a leaf child (BVH4Node::tlp, Hit::tlp) carries the shade-queue class of the object's material in
+// its top bits, so that k_trace can bin a finished ray without another lookup: word = class << 28 | object index.
+#define RT_TLP_MASK 0x01FFFFFFu   // 2^25 top-level objects (a packed hit is index | face << 25 | class << 28)
+RT_D int tlp_index(int word) { return word & (int)RT_TLP_MASK; }
+RT_D int tlp_class(int word) { return (word >> 28) & 7; }
+
 RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int face, Hit& best) {
   if (t < best.t) { best.t = t; best.tlp = (int)tlp; best.face = face; return; }
   if (best.tlp < 0) {  // t == the caller's t_max: only an inclusive test accepts that (quad.cuh:64 vs sphere.cuh:63)
@@ -263,126 +269,159 @@ RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int 
     return;
   }
   // exact tie (t == best.t; only inclusive tests get here): order semantics of bvh_node::hit
-  const int rn = S.tlp[tlp].rank, rb = S.tlp[best.tlp].rank;
-  const bool take = (rn > rb) ? ref_inclusive(S, ref) : !ref_inclusive(S, S.tlp[best.tlp].ref);
+  const int rn = S.tlp[tlp_index((int)tlp)].rank, rb = S.tlp[tlp_index(best.tlp)].rank;
+  const bool take = (rn > rb) ? ref_inclusive(S, ref) : !ref_inclusive(S, S.tlp[tlp_index(best.tlp)].ref);
   if (take) { best.t = t; best.tlp = (int)tlp; best.face = face; }
 }
 
-RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
-  Hit best; best.t = tmax0; best.tlp = -1; best.face = 0;
-  const float ix = frcp(r.d.x), iy = frcp(r.d.y), iz = frcp(r.d.z);  // 1.0f / direction, aabb.cuh:48
-  // float4 index of the NEAR plane vector of each axis inside a node (lox 0, loy 1, loz 2, hix 3, hiy 4, hiz 5)
-  const int onx = ix < 0.0f ? 3 : 0, ony = iy < 0.0f ? 4 : 1, onz = iz < 0.0f ? 5 : 2;
-  uint32_t stack[RT_STACK];  // interior nodes only
-  uint32_t lq_ref[RT_LEAFQ], lq_tlp[RT_LEAFQ];
-  float lq_tn[RT_LEAFQ];
-  int sp = 0, nl = 0;
-  uint32_t cur = 0;
-  bool have = active;
-  while (true) {
-    const bool can = have && nl <= RT_LEAFQ - 4;
-    const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
-    const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, nl > 0);
-    if ((mexp | mleaf) == 0u) break;
-    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !have && nl > 0);  // traversal done, leaves pending
-    if (mleaf == 0u || (__popc(mexp) >= RT_NODE_MIN && __popc(mwait) < RT_LEAF_WAIT_MAX)) {
-      // ---------------- node phase ----------------
-      if ((threadIdx.x & 31) == 0) RT_COUNT(4, 1);
-#ifdef RT_STATS
-      { const unsigned mfin = __ballot_sync(0xFFFFFFFFu, !have && nl == 0); const unsigned mblk = __ballot_sync(0xFFFFFFFFu, have && !can); if ((threadIdx.x & 31) == 0) { atomicAdd(&g_stats2[0], (unsigned long long)__popc(mfin)); atomicAdd(&g_stats2[1], (unsigned long long)__popc(mblk)); atomicAdd(&g_stats2[2], (unsigned long long)__popc(mexp)); } }
-#endif
-      if (can) {
-        RT_COUNT(0, 1);
-        const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
-        // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0. The swap is
-        // done by the LOAD: per-ray offsets pick the near / far plane vectors of the node, no per-child selects.
-        const float4 nxp = __ldg(np + onx), fxp = __ldg(np + (3 - onx));
-        const float4 nyp = __ldg(np + ony), fyp = __ldg(np + (5 - ony));
-        const float4 nzp = __ldg(np + onz), fzp = __ldg(np + (7 - onz));
-        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
-        const uint4 tl = __ldg(reinterpret_cast<const uint4*>(np + 7));
-        const float ax[4] = {nxp.x, nxp.y, nxp.z, nxp.w}, bx[4] = {fxp.x, fxp.y, fxp.z, fxp.w};
-        const float ay[4] = {nyp.x, nyp.y, nyp.z, nyp.w}, by[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
-        const float az[4] = {nzp.x, nzp.y, nzp.z, nzp.w}, bz[4] = {fzp.x, fzp.y, fzp.z, fzp.w};
-        const uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w}, ct[4] = {tl.x, tl.y, tl.z, tl.w};
-        uint32_t key[4];  // interior children that are entered: (entry distance bits, child slot); else 0xFFFFFFFF
+// The per-lane arrays live OUTSIDE Trav (a struct with dynamically indexed arrays is kept in local memory as a whole:
+// 84 LDL / 58 STL in k_trace instead of 20 / 15) and are handed to the phases by pointer.
+#define RT_TRAV_ARRAYS(name) uint32_t name##_stack[RT_STACK], name##_lq_ref[RT_LEAFQ], name##_lq_tlp[RT_LEAFQ]; float name##_lq_tn[RT_LEAFQ]
+#define RT_TRAV_ARGS(name) name##_stack, name##_lq_ref, name##_lq_tlp, name##_lq_tn
+
+// Per-lane traversal state. The warp-level driver (closest_hit below for one ray per lane; k_trace's loop, which also
+// refills finished lanes with new rays) decides by ballot which phase runs next.
+struct Trav {
+  Ray r;
+  float ix, iy, iz;      // 1.0f / direction, aabb.cuh:48
+  float tmin;
+  Hit best;
+  int sp, nl;
+  uint32_t cur;
+  bool have;             // holds a node to expand
+
+  RT_D void reset() { have = false; nl = 0; sp = 0; cur = 0; best.t = FLT_MAX; best.tlp = -1; best.face = 0; }
+  RT_D void begin(const Ray& ray, float tmin_, float tmax0) {
+    r = ray; tmin = tmin_;
+    best.t = tmax0; best.tlp = -1; best.face = 0;
+    ix = frcp(r.d.x); iy = frcp(r.d.y); iz = frcp(r.d.z);
+    sp = 0; nl = 0; cur = 0; have = true;
+  }
+  RT_D bool can_expand() const { return have && nl <= RT_LEAFQ - 4; }
+  RT_D bool finished() const { return !have && nl == 0; }
+
+  // ---------------- node phase (lanes with can_expand()) ----------------
+  RT_D void node_step(const DScene& S, unsigned int* overflow, uint32_t* stack, uint32_t* lq_ref, uint32_t* lq_tlp, float* lq_tn) {
+    RT_COUNT(0, 1);
+    const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
+    // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0. The swap is
+    // done by the LOAD: per-ray offsets pick the near / far plane vectors of the node, no per-child selects.
+    // float4 index of the NEAR plane vector of each axis inside a node (lox 0, loy 1, loz 2, hix 3, hiy 4, hiz 5)
+    const int onx = ix < 0.0f ? 3 : 0, ony = iy < 0.0f ? 4 : 1, onz = iz < 0.0f ? 5 : 2;
+    const float4 nxp = __ldg(np + onx), fxp = __ldg(np + (3 - onx));
+    const float4 nyp = __ldg(np + ony), fyp = __ldg(np + (5 - ony));
+    const float4 nzp = __ldg(np + onz), fzp = __ldg(np + (7 - onz));
+    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+    const uint4 tl = __ldg(reinterpret_cast<const uint4*>(np + 7));
+    const float ax[4] = {nxp.x, nxp.y, nxp.z, nxp.w}, bx[4] = {fxp.x, fxp.y, fxp.z, fxp.w};
+    const float ay[4] = {nyp.x, nyp.y, nyp.z, nyp.w}, by[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
+    const float az[4] = {nzp.x, nzp.y, nzp.z, nzp.w}, bz[4] = {fzp.x, fzp.y, fzp.z, fzp.w};
+    const uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w}, ct[4] = {tl.x, tl.y, tl.z, tl.w};
+    uint32_t key[4];  // interior children that are entered: (entry distance bits, child slot); else 0xFFFFFFFF
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // tmin = t0 > tmin ? t0 : tmin (== fmaxf, NaN keeps tmin); reject when tmax <= tmin.
-          float lo = fmaxf(fmul(fsub(ax[c], r.o.x), ix), tmin), hi = fminf(fmul(fsub(bx[c], r.o.x), ix), best.t);
-          lo = fmaxf(fmul(fsub(ay[c], r.o.y), iy), lo); hi = fminf(fmul(fsub(by[c], r.o.y), iy), hi);
-          lo = fmaxf(fmul(fsub(az[c], r.o.z), iz), lo); hi = fminf(fmul(fsub(bz[c], r.o.z), iz), hi);
-          const bool entered = hi > lo && cr[c] != RT_NODE_EMPTY;
-          const bool interior = (cr[c] & RT_NODE_FLAG) != 0;
-          // lo >= tmin > 0, so its bit pattern orders like the float; the low two mantissa bits carry the child slot
-          key[c] = (entered && interior) ? ((__float_as_uint(lo) & ~3u) | (uint32_t)c) : 0xFFFFFFFFu;
-          if (entered && !interior) { lq_ref[nl] = cr[c]; lq_tlp[nl] = ct[c]; lq_tn[nl] = lo; ++nl; }  // leaves need no order
-        }
-        // interior children: nearest is the next node, the others are stacked far-to-near (5-comparator network on keys)
+    for (int c = 0; c < 4; ++c) {
+      // tmin = t0 > tmin ? t0 : tmin (== fmaxf, NaN keeps tmin); reject when tmax <= tmin.
+      float lo = fmaxf(fmul(fsub(ax[c], r.o.x), ix), tmin), hi = fminf(fmul(fsub(bx[c], r.o.x), ix), best.t);
+      lo = fmaxf(fmul(fsub(ay[c], r.o.y), iy), lo); hi = fminf(fmul(fsub(by[c], r.o.y), iy), hi);
+      lo = fmaxf(fmul(fsub(az[c], r.o.z), iz), lo); hi = fminf(fmul(fsub(bz[c], r.o.z), iz), hi);
+      const bool entered = hi > lo && cr[c] != RT_NODE_EMPTY;
+      const bool interior = (cr[c] & RT_NODE_FLAG) != 0;
+      // lo >= tmin > 0, so its bit pattern orders like the float; the low two mantissa bits carry the child slot
+      key[c] = (entered && interior) ? ((__float_as_uint(lo) & ~3u) | (uint32_t)c) : 0xFFFFFFFFu;
+      if (entered && !interior) { lq_ref[nl] = cr[c]; lq_tlp[nl] = ct[c]; lq_tn[nl] = lo; ++nl; }  // leaves need no order
+    }
+    // interior children: nearest is the next node, the others are stacked far-to-near (5-comparator network on keys)
 #define RT_KSWAP(a, b) do { const uint32_t lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; } while (0)
-        RT_KSWAP(0, 1); RT_KSWAP(2, 3); RT_KSWAP(0, 2); RT_KSWAP(1, 3); RT_KSWAP(1, 2);
+    RT_KSWAP(0, 1); RT_KSWAP(2, 3); RT_KSWAP(0, 2); RT_KSWAP(1, 3); RT_KSWAP(1, 2);
 #undef RT_KSWAP
+    if (sp > RT_STACK - 3) { atomicOr(overflow, 1u); sp = RT_STACK - 3; }  // rt_render fails when the flag is set
 #pragma unroll
-        for (int k = 3; k >= 1; --k) {
-          if (key[k] != 0xFFFFFFFFu) {
-            const uint32_t i = key[k] & 3u;
-            const uint32_t c = (i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0]);
-            if (sp < RT_STACK) stack[sp++] = c & 0x7FFFFFFFu; else atomicOr(overflow, 1u);
-          }
-        }
-        uint32_t next = RT_NODE_EMPTY;
-        if (key[0] != 0xFFFFFFFFu) {
-          const uint32_t i = key[0] & 3u;
-          next = ((i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0])) & 0x7FFFFFFFu;
-        }
-        if (next != RT_NODE_EMPTY) cur = next;
-        else if (sp > 0) cur = stack[--sp];
-        else have = false;
+    for (int k = 3; k >= 1; --k) {
+      if (key[k] != 0xFFFFFFFFu) {
+        const uint32_t i = key[k] & 3u;
+        const uint32_t c = (i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0]);
+        stack[sp++] = c & 0x7FFFFFFFu;
       }
-    } else {
-      // ---------------- leaf phase ----------------
-      if ((threadIdx.x & 31) == 0) RT_COUNT(5, 1);
-      RT_COUNT(6, nl);
-      const int nmax = __reduce_max_sync(0xFFFFFFFFu, nl);
-      // spheres
+    }
+    uint32_t next = RT_NODE_EMPTY;
+    if (key[0] != 0xFFFFFFFFu) {
+      const uint32_t i = key[0] & 3u;
+      next = ((i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0])) & 0x7FFFFFFFu;
+    }
+    if (next != RT_NODE_EMPTY) cur = next;
+    else if (sp > 0) cur = stack[--sp];
+    else have = false;
+  }
+
+  // ---------------- leaf phase (the whole warp) ----------------
+  RT_D void leaf_phase(const DScene& S, const uint32_t* lq_ref, const uint32_t* lq_tlp, const float* lq_tn) {
+    RT_COUNT(6, nl);
+    const int nmax = __reduce_max_sync(0xFFFFFFFFu, nl);
+    // spheres
+    for (int k = 0; k < nmax; ++k) {
+      if (k < nl && ref_type(lq_ref[k]) == G_SPHERE && lq_tn[k] < best.t) {
+        float t; V3 cc;
+        RT_COUNT(1, 1);
+        if (sphere_t<true>(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
+      }
+    }
+    // quads, boxes, instances: every lane walks ITS geometry leaves with its own cursor, so that the j-th box test of
+    // all lanes runs in the same iteration (a shared position index left 6 of 32 lanes active in the box code)
+    {
+      int kk = 0;
+      while (true) {
+        while (kk < nl && ref_type(lq_ref[kk]) == G_SPHERE || kk < nl && ref_type(lq_ref[kk]) == G_MEDIUM) ++kk;
+        const bool has = kk < nl;
+        if (__ballot_sync(0xFFFFFFFFu, has) == 0u) break;
+        if (has && lq_tn[kk] < best.t) {
+          Rec rec; rec.face = 0;
+          RT_COUNT(2, 1);
+          if (geom_hit<false, true>(S, lq_ref[kk], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[kk], lq_tlp[kk], rec.t, rec.face, best);
+        }
+        ++kk;
+      }
+    }
+    // media
+    const unsigned mmed = __ballot_sync(0xFFFFFFFFu, [&] { bool any = false; for (int k = 0; k < nl; ++k) any |= ref_type(lq_ref[k]) == G_MEDIUM; return any; }());
+    if (mmed) {
       for (int k = 0; k < nmax; ++k) {
-        if (k < nl && ref_type(lq_ref[k]) == G_SPHERE && lq_tn[k] < best.t) {
-          float t; V3 cc;
-          RT_COUNT(1, 1);
-          if (sphere_t<true>(S.spheres[ref_index(lq_ref[k])], r, tmin, best.t, t, cc)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
+        if (k < nl && ref_type(lq_ref[k]) == G_MEDIUM && lq_tn[k] < best.t) {
+          float t;
+          RT_COUNT(3, 1);
+          if (medium_hit(S, S.media[ref_index(lq_ref[k])], r, tmin, best.t, t)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
         }
       }
-      // quads, boxes, instances: every lane walks ITS geometry leaves with its own cursor, so that the j-th box test of
-      // all lanes runs in the same iteration (a shared position index left 6 of 32 lanes active in the box code)
-      {
-        int kk = 0;
-        while (true) {
-          while (kk < nl && ref_type(lq_ref[kk]) == G_SPHERE || kk < nl && ref_type(lq_ref[kk]) == G_MEDIUM) ++kk;
-          const bool has = kk < nl;
-          if (__ballot_sync(0xFFFFFFFFu, has) == 0u) break;
-          if (has && lq_tn[kk] < best.t) {
-            Rec rec; rec.face = 0;
-            RT_COUNT(2, 1);
-            if (geom_hit<false, true>(S, lq_ref[kk], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[kk], lq_tlp[kk], rec.t, rec.face, best);
-          }
-          ++kk;
-        }
-      }
-      // media
-      const unsigned mmed = __ballot_sync(0xFFFFFFFFu, [&] { bool any = false; for (int k = 0; k < nl; ++k) any |= ref_type(lq_ref[k]) == G_MEDIUM; return any; }());
-      if (mmed) {
-        for (int k = 0; k < nmax; ++k) {
-          if (k < nl && ref_type(lq_ref[k]) == G_MEDIUM && lq_tn[k] < best.t) {
-            float t;
-            RT_COUNT(3, 1);
-            if (medium_hit(S, S.media[ref_index(lq_ref[k])], r, tmin, best.t, t)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
-          }
-        }
-      }
-      nl = 0;
+    }
+    nl = 0;
+  }
+
+  // Which phase next? Node phase unless too few lanes can expand a node or too many only wait for their leaves.
+  RT_D static bool pick_node_phase(unsigned mexp, unsigned mleaf, unsigned mwait) {
+    return mleaf == 0u || (__popc(mexp) >= RT_NODE_MIN && __popc(mwait) < RT_LEAF_WAIT_MAX);
+  }
+};
+
+// One ray per lane, no refill (k_aov): the whole warp calls it, lanes without a ray pass active = false.
+RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
+  Trav T;
+  RT_TRAV_ARRAYS(m);
+  T.reset();
+  if (active) T.begin(r, tmin, tmax0);
+  while (true) {
+    const bool can = T.can_expand();
+    const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
+    const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, T.nl > 0);
+    if ((mexp | mleaf) == 0u) break;
+    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have && T.nl > 0);  // traversal done, leaves pending
+    if (Trav::pick_node_phase(mexp, mleaf, mwait)) {
+      if ((threadIdx.x & 31) == 0) RT_COUNT(4, 1);
+      if (can) T.node_step(S, overflow, RT_TRAV_ARGS(m));
+    } else {
+      if ((threadIdx.x & 31) == 0) RT_COUNT(5, 1);
+      T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn);
     }
   }
-  return best;
+  return T.best;
 }
 
 }  // namespace rt

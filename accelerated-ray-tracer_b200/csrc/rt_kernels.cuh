@@ -2,51 +2,66 @@
 //
 // The reference renders with ONE megakernel: a thread per pixel loops ns samples x <= 50 bounces
 // through virtual calls and device recursion (render/color, main.cu:44-133). Here the same
-// integrator runs as waves over a pool of path slots kept in SoA arrays in HBM/L2:
+// integrator runs as waves over a pool of paths whose state STREAMS through two ping-pong sets of
+// SoA arrays in HBM/L2 (no persistent slots, no gathers through an indirection table):
 //
-//   k_init     slot state: "needs a sample"; reference-RNG mode: XORWOW seeding      (render_init, main.cu:96-105)
-//   k_trace    one thread per SLOT (coalesced state access, no ray lists): a slot whose sample has ended
-//              takes its next camera sample here (path regeneration, main.cu:119-123), then the closest
-//              hit over the 4-wide BVH; paths are binned by the hit material class into shade queues
-//              (per-block aggregation, one global atomic per class per block)        (main.cu:57; bvh.cuh:95)
-//   k_shade    one material class per warp: miss/background, emission, scatter, throughput; a finished
-//              sample is added to its pixel and the slot is flagged "needs a sample"  (main.cu:58-83, 124)
+//   k_init     the first n_slots camera samples (render_init + main.cu:119-123); reference-RNG mode: XORWOW seeding
+//   k_trace    pure closest-hit kernel (main.cu:57; bvh.cuh:95). A WARP owns RT_RANGE consecutive rays of the wave's
+//              dense layout and runs them through the 4-wide BVH with lane refill: a lane whose ray is finished takes
+//              the next ray of the warp's range, so the warp-wide node / leaf phases stay full until the range is
+//              drained. No block-level barrier anywhere. At the end the warp bins its rays by the material class of
+//              the hit into shade queues (one atomic per class per warp, spread over RT_NSUB sub-queues).
+//   k_shade    one material class per warp, reading the path state in queue order (neighbouring entries were written
+//              by neighbouring trace lanes): miss/background, emission, scatter, throughput (main.cu:58-83). A finished
+//              sample is added to its pixel and the lane takes the NEXT camera sample right away (path regeneration,
+//              main.cu:119-124); the new state is written densely at the thread's own position of the other
+//              ping-pong set, which is the layout the next k_trace walks.
 //   k_accumulate / k_resolve   sums -> linear accumulation buffer -> 1/ns, gamma     (main.cu:128-132)
 //   k_aov      primary-hit object/material id + t for the centre ray of every pixel
 //
-// Philox mode (production): a slot is a worker. Work item w = sample * n_local_pixels + local_pixel is
-// handed out by one 64-bit counter (one atomic per block, at the head of k_trace), so every slot stays
+// Philox mode (production): a path is a worker. Work item w = sample * n_local_pixels + local_pixel is
+// handed out by one 64-bit counter (one atomic per warp that finished samples), so every lane stays
 // busy until the whole job is done no matter how unevenly path lengths are spread over the image (on
-// the Book-2 final scene a pixel-bound scheme ran at 11% mean slot occupancy). A finished sample is
+// the Book-2 final scene a pixel-bound scheme ran at 11% mean occupancy). A finished sample is
 // added to its pixel with 64-bit FIXED-POINT atomics (2^-32 resolution): integer sums do not depend on
 // the order of arrival, so the image is bit-reproducible and identical under any tile split.
-// Reference-RNG mode (validation): a slot IS a pixel and consumes that pixel's XORWOW stream in exactly
+// Reference-RNG mode (validation): a path IS a pixel and consumes that pixel's XORWOW stream in exactly
 // the reference's order, samples one after the other, summed in float like `col += color(...)`.
 #pragma once
 #include "rt_shade.cuh"
 
 namespace rt {
 
+#ifndef RT_NSUB
+#define RT_NSUB 4                       // sub-queues per material class: spreads the per-warp queue atomics over 4 addresses
+#endif
+#define RT_NQ (Q_COUNT * RT_NSUB)       // shade queues of a wave (<= 32: k_shade scans them with one warp scan)
+#ifndef RT_RANGE
+#define RT_RANGE 64                     // consecutive rays of the dense layout a trace warp owns (A/B on C4: 32 -4%, 128 -2%)
+#endif
+#define RT_RANGE_K (RT_RANGE / 32)
+
 struct PathArrays {
-  float4* ray_o;   // origin.xyz, time
-  float4* ray_d;   // direction.xyz, local pixel (int bits)
-  float2* hit;     // t, (box face << 28 | top-level object index) as int bits; -1 = miss
-  float4* thr;     // throughput.rgb, bounce (int bits); bounce = SLOT_NEEDS_SAMPLE / SLOT_DEAD are slot states
-  float4* rad;     // radiance.rgb of the current sample, sample number (int bits)
-  float4* col;     // reference-RNG mode: float sum of the pixel's finished samples
-  uint32_t* rng;   // reference-RNG mode: 6 words per slot, SoA [6][n_slots]
+  float4* ray_o[2];  // origin.xyz, time                                    [2]: ping-pong sets, k_shade reads [parity], writes [parity ^ 1]
+  float4* ray_d[2];  // direction.xyz, local pixel (int bits; < 0 = hole: no path at this position)
+  float4* thr[2];    // throughput.rgb, bounce (int bits)
+  float4* rad[2];    // radiance.rgb of the current sample, sample number (int bits)
+  float2* hit;       // k_trace -> k_shade: t, packed hit (object | face << 25 | class << 28; -1 miss; -2 hole)
+  float4* col;       // reference-RNG mode: float sum of the pixel's finished samples (per local pixel)
+  uint32_t* rng;     // reference-RNG mode: 6 words per local pixel, SoA [6][n_slots]
   unsigned long long* acc64;  // Philox mode: per local pixel 3 x fixed-point (2^-32) radiance sums
-  int* order;      // k_trace thread -> slot: the previous wave's shade-queue layout (-1 = hole), see k_shade
-  unsigned long long* next_work;  // Philox mode: next work item to hand out (shared by all slot pools)
+  unsigned long long* next_work;  // Philox mode: next work item to hand out (shared by all pools)
+  int* queues;       // [RT_NQ][subcap] positions of the dense layout, by (class, sub-queue)
+  int subcap;
 };
 
 struct WaveCounters {
-  int n_queue[2][Q_COUNT + 1]; // shade queue fill, by wave parity (their sum = rays traced in that wave)
-  int order_len;               // entries of PathArrays::order in use
-  unsigned long long rays;     // closest-hit queries issued (= the reference's bounce-loop iterations)
-  unsigned long long samples;  // finished samples
+  int n_queue[2][RT_NQ];       // shade queue fill, by wave parity (their sum = rays traced in that wave)
+  int order_len;               // length of the dense layout the next k_trace walks
   unsigned int overflow;       // traversal stack overflow flag (must stay 0)
-  unsigned int nonfinite;      // Philox mode: samples dropped because their radiance was inf/NaN
+  unsigned int nonfinite;      // Philox mode: samples dropped because their radiance was inf/NaN/out of fixed-point range
+  unsigned int pad;
+  unsigned long long rays;     // closest-hit queries issued (= the reference's bounce-loop iterations)
 };
 
 struct RenderParams {
@@ -54,7 +69,7 @@ struct RenderParams {
   float inv_nx;          // 1.0f / nx
   int rows_local;        // scanlines owned by this rank (tile split: j = lr * world + rank)
   int rank, world;
-  int n_slots;           // path slots in flight (reference-RNG mode: one per local pixel)
+  int n_slots;           // paths in flight (reference-RNG mode: one per local pixel)
   long long work_total;  // rows_local * nx * sample_count work items (Philox mode)
   int sample_base;       // first sample number of this rank's share (spp split), else 0
   int sample_count;      // samples per pixel this rank renders
@@ -65,7 +80,8 @@ struct RenderParams {
 };
 
 enum RngMode : int { RNG_PHILOX = 0, RNG_REFERENCE = 1 };
-enum SlotState : int { SLOT_NEEDS_SAMPLE = -1, SLOT_DEAD = -2 };
+#define RT_HIT_MISS (-1)
+#define RT_HIT_HOLE (-2)
 
 struct SlotInfo { int lpix, i, j, pix; };
 RT_D SlotInfo pixel_info(const RenderParams& P, int lpix) {
@@ -86,72 +102,48 @@ template <int MODE> struct RngOf;
 template <> struct RngOf<RNG_PHILOX> { typedef Philox type; };
 template <> struct RngOf<RNG_REFERENCE> { typedef Xorwow type; };
 
-template <int MODE>
-RT_D void rng_load(typename RngOf<MODE>::type& g, const PathArrays& A, const RenderParams& P, int slot, int pix, int sample, int stage);
-template <>
-RT_D void rng_load<RNG_PHILOX>(Philox& g, const PathArrays&, const RenderParams& P, int, int pix, int sample, int stage) {
+RT_D void rng_load(Philox& g, const PathArrays&, const RenderParams& P, int, int pix, int sample, int stage) {
   g.init(P.seed, (uint32_t)pix, (uint32_t)sample, (uint32_t)stage);
 }
-template <>
-RT_D void rng_load<RNG_REFERENCE>(Xorwow& g, const PathArrays& A, const RenderParams& P, int slot, int, int, int) {
+RT_D void rng_load(Xorwow& g, const PathArrays& A, const RenderParams& P, int lpix, int, int, int) {
   const int n = P.n_slots;
-  g.d = A.rng[slot]; g.v0 = A.rng[n + slot]; g.v1 = A.rng[2 * n + slot]; g.v2 = A.rng[3 * n + slot];
-  g.v3 = A.rng[4 * n + slot]; g.v4 = A.rng[5 * n + slot];
+  g.d = A.rng[lpix]; g.v0 = A.rng[n + lpix]; g.v1 = A.rng[2 * n + lpix]; g.v2 = A.rng[3 * n + lpix];
+  g.v3 = A.rng[4 * n + lpix]; g.v4 = A.rng[5 * n + lpix];
 }
 RT_D void rng_store(const Philox&, const PathArrays&, const RenderParams&, int) {}
-RT_D void rng_store(const Xorwow& g, const PathArrays& A, const RenderParams& P, int slot) {
+RT_D void rng_store(const Xorwow& g, const PathArrays& A, const RenderParams& P, int lpix) {
   const int n = P.n_slots;
-  A.rng[slot] = g.d; A.rng[n + slot] = g.v0; A.rng[2 * n + slot] = g.v1; A.rng[3 * n + slot] = g.v2;
-  A.rng[4 * n + slot] = g.v3; A.rng[5 * n + slot] = g.v4;
+  A.rng[lpix] = g.d; A.rng[n + lpix] = g.v0; A.rng[2 * n + lpix] = g.v1; A.rng[3 * n + lpix] = g.v2;
+  A.rng[4 * n + lpix] = g.v3; A.rng[5 * n + lpix] = g.v4;
 }
 
-// New camera sample for a slot (main.cu:121-123): jitter, lens, shutter time; throughput 1, radiance 0.
+// New camera sample (main.cu:121-123): jitter, lens, shutter time; throughput 1, radiance 0. Written at position
+// `at` of ping-pong set `pp`; ray_d.w carries the local pixel, rad.w the sample number.
 template <class RNG>
-RT_D Ray start_sample(const DScene& S, const RenderParams& P, const PathArrays& A, int slot, const SlotInfo& si, int sample, RNG& g) {
-  // ray_d.w carries the slot's local pixel, rad.w its sample number
+RT_D void start_sample(const DScene& S, const RenderParams& P, const PathArrays& A, int pp, int at, const SlotInfo& si, int sample, RNG& g) {
   const float u = fdiv(fadd((float)si.i, g.uniform()), (float)P.nx);
   const float v = fdiv(fadd((float)si.j, g.uniform()), (float)P.ny);
   const Ray r = camera_get_ray(S.cam, u, v, g);
-  A.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
-  A.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(si.lpix));
-  A.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
-  A.rad[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(sample));
-  return r;
+  A.ray_o[pp][at] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
+  A.ray_d[pp][at] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(si.lpix));
+  A.thr[pp][at] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
+  A.rad[pp][at] = make_float4(0.f, 0.f, 0.f, __int_as_float(sample));
 }
+RT_D void write_hole(const PathArrays& A, int pp, int at) { A.ray_d[pp][at] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); }
 
-// Block-aggregated reservation: EVERY thread of the block calls it; threads with `pred` get consecutive
-// positions starting at a base taken with ONE global atomic per block (a wave of 1 Mi rays appends to a single
-// counter: one atomic per warp serialised 32 Ki same-address atomics in L2 and cost ~40% of k_shade, profiles/r01).
 #ifndef RT_BLOCK
 #define RT_BLOCK 256
 #endif
 #ifndef RT_SHADE_MINB
 #define RT_SHADE_MINB 3   // resident blocks per SM the shade kernel is compiled for (register cap 65536 / (256 * MINB))
 #endif
-#define RT_WARPS (RT_BLOCK / 32)
 #ifndef RT_TBLOCK
-#define RT_TBLOCK 256     // k_trace block size
+#define RT_TBLOCK 64      // k_trace block size: no block-level synchronisation, so small blocks retire warp by warp
 #endif
 #define RT_TWARPS (RT_TBLOCK / 32)
-template <int NW, class T>
-RT_D T block_reserve(T* counter, bool pred, int* s_cnt /*[NW]*/, T* s_base) {
-  const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_cnt[warp] = __popc(m);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
-    *s_base = tot > 0 ? atomicAdd(counter, (T)tot) : (T)0;
-  }
-  __syncthreads();
-  const T pos = *s_base + (T)(s_cnt[warp] + __popc(m & ((1u << lane) - 1u)));
-  __syncthreads();  // s_cnt / s_base may be reused by the next call
-  return pos;
-}
 
 #define RT_FIXED_ONE 4294967296.0f  /* 2^32 */
+#define RT_FIXED_MAX 1048576.0f     /* samples at or above 2^20 are counted as dropped: 2^11 of them still fit the Q31.32 sum */
 RT_D void fixed_add(unsigned long long* acc, float v) {
   atomicAdd(acc, (unsigned long long)__float2ll_rn(v * RT_FIXED_ONE));  // two's complement: negative values add correctly
 }
@@ -169,203 +161,276 @@ RT_D void work_to_pixel_sample(const RenderParams& P, unsigned long long w, int&
   }
 }
 
-// Slot state before the first wave: every slot needs a sample. Reference-RNG mode also seeds the pixel's stream
-// (render_init, main.cu:104) and zeroes its float sum; rad.w = the sample number BEFORE the first one.
+// The first wave: position = slot. Philox mode: work item = work_base + slot (the host starts the work counter behind them);
+// reference-RNG mode: slot = local pixel, its stream is seeded (render_init, main.cu:104) and draws its first sample.
 template <int MODE>
-__global__ void __launch_bounds__(RT_BLOCK) k_init(RenderParams P, PathArrays A) {
+__global__ void __launch_bounds__(RT_BLOCK) k_init(DScene S, RenderParams P, PathArrays A, int work_base) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= P.n_slots) return;
-  A.order[slot] = slot;  // first wave: identity (the host sets order_len = n_slots)
-  A.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)SLOT_NEEDS_SAMPLE));
-  A.rad[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(P.sample_base - 1));
   if constexpr (MODE == RNG_REFERENCE) {
-    const SlotInfo si = pixel_info(P, slot);  // slot == local pixel
+    const SlotInfo si = pixel_info(P, slot);
     A.col[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     Xorwow g;
     g.init((unsigned long long)(long long)(1984 + si.pix));
+    start_sample(S, P, A, 0, slot, si, P.sample_base, g);
     rng_store(g, A, P, slot);
+  } else {
+    int lpix, sample;
+    work_to_pixel_sample(P, (unsigned long long)(work_base + slot), lpix, sample);
+    const SlotInfo si = pixel_info(P, lpix);
+    Philox g;
+    rng_load(g, A, P, lpix, si.pix, sample, 0);
+    start_sample(S, P, A, 0, slot, si, sample, g);
   }
 }
 
 #ifndef RT_TRACE_MINB
-#define RT_TRACE_MINB 4     // resident k_trace blocks per SM the kernel is compiled for (64 registers)
+#define RT_TRACE_MINB (2048 / RT_TBLOCK / 2)  // resident k_trace blocks per SM the kernel is compiled for: 32 warps, 64 registers
 #endif
-template <int MODE>
-__global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, RenderParams P, PathArrays A, int* __restrict__ queues,
-                                                     WaveCounters* C, int parity) {
-  __shared__ int s_cnt[RT_TWARPS];
-  __shared__ unsigned long long s_wbase;
-  __shared__ int s_q[RT_TWARPS][Q_COUNT];
-  __shared__ int s_qbase[Q_COUNT];
-  // Thread -> slot through the previous wave's queue layout: paths that hit the same material class sit next to
-  // each other, and the primary rays regenerated behind the miss / light queues come out in pixel order, which
-  // keeps warps far more coherent than slot order (measured: 0.32 ms vs 0.53 ms per 1 Mi-ray wave on C4).
-  // No early exit: closest_hit is warp-wide, the binning block-wide.
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  int slot = -1;
-  if (gid < C->order_len) slot = A.order[gid];
-  const bool in_range = slot >= 0;
-  int state = SLOT_DEAD;
-  if (in_range) state = __float_as_int(A.thr[slot].w);
-  bool active = state >= 0;
-  Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
-  // ---- path regeneration (main.cu:119-123): a slot whose sample has ended takes the next one ----
-  const bool need = state == SLOT_NEEDS_SAMPLE;
-  if constexpr (MODE == RNG_PHILOX) {
-    const unsigned long long w = block_reserve<RT_TWARPS>(A.next_work, need, s_cnt, &s_wbase);
-    if (need) {
-      if (w < (unsigned long long)P.work_total) {
-        int lpix, sample;
-        work_to_pixel_sample(P, w, lpix, sample);
-        const SlotInfo si = pixel_info(P, lpix);
-        Philox g;
-        rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-        r = start_sample(S, P, A, slot, si, sample, g);
-        active = true;
-      } else {
-        A.thr[slot].w = __int_as_float((int)SLOT_DEAD);
+#ifndef RT_REFILL_MIN
+#define RT_REFILL_MIN 32    // finished lanes that trigger a refill from the warp's range (A/B on C4: 8 -9%, 16 -6%: refilled lanes
+                            // start at the root while the others are deep in the tree, which desynchronises the warp-wide phases)
+#endif
+__global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, float tmin, const float4* ray_o, const float4* ray_d,
+                                                                    float2* hit, int* queues, int subcap, WaveCounters* C, int parity) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int order_len = C->order_len;
+  const int base = wid * RT_RANGE;
+  if (base >= order_len) return;
+  const int end = min(base + RT_RANGE, order_len);
+  int next = base;  // warp-uniform: first ray of the range nobody has taken yet
+  int gid = -1;     // the ray this lane is tracing
+  Trav T;
+  RT_TRAV_ARRAYS(m);
+  T.reset();
+  while (true) {
+    const bool fin = T.finished();
+    const unsigned mfin = __ballot_sync(0xFFFFFFFFu, fin);
+    if (mfin == 0xFFFFFFFFu || (next < end && __popc(mfin) >= RT_REFILL_MIN)) {
+      // ---------------- refill: finished lanes store their hit and take the next rays of the range ----------------
+      if (fin) {
+        if (gid >= 0) {
+          const int packed = T.best.tlp < 0 ? RT_HIT_MISS : (tlp_index(T.best.tlp) | (T.best.face << 25) | (tlp_class(T.best.tlp) << 28));
+          hit[gid] = make_float2(T.best.t, __int_as_float(packed));
+          gid = -1;
+        }
+        const int g = next + __popc(mfin & lt);
+        if (g < end) {
+          const float4 d = ray_d[g];
+          if (__float_as_int(d.w) >= 0) {
+            const float4 o = ray_o[g];
+            Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+            T.begin(r, tmin, FLT_MAX);
+            gid = g;
+          } else {
+            hit[g] = make_float2(0.f, __int_as_float(RT_HIT_HOLE));
+          }
+        }
       }
+      if (next >= end) break;  // everyone finished and the range is drained
+      next += __popc(mfin);
+      continue;
     }
-  } else {
-    if (need) {
-      const int sample = __float_as_int(A.rad[slot].w) + 1;
-      if (sample < P.sample_base + P.sample_count) {
-        const SlotInfo si = pixel_info(P, slot);
-        Xorwow g;
-        rng_load<MODE>(g, A, P, slot, si.pix, sample, 0);
-        r = start_sample(S, P, A, slot, si, sample, g);
-        rng_store(g, A, P, slot);
-        active = true;
-      } else {
-        A.thr[slot].w = __int_as_float((int)SLOT_DEAD);
-      }
+    const bool can = T.can_expand();
+    const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
+    const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, T.nl > 0);
+    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have && T.nl > 0);  // traversal done, leaves pending
+    if (Trav::pick_node_phase(mexp, mleaf, mwait)) {
+      if (lane == 0) RT_COUNT(4, 1);
+#ifdef RT_STATS
+      { const unsigned mblk = __ballot_sync(0xFFFFFFFFu, T.have && !can); if (lane == 0) { atomicAdd(&g_stats2[0], (unsigned long long)__popc(mfin)); atomicAdd(&g_stats2[1], (unsigned long long)__popc(mblk)); atomicAdd(&g_stats2[2], (unsigned long long)__popc(mexp)); } }
+#endif
+      if (can) T.node_step(S, &C->overflow, RT_TRAV_ARGS(m));
+    } else {
+      if (lane == 0) RT_COUNT(5, 1);
+      T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn);
     }
   }
-  if (active && !need) {
-    const float4 o = A.ray_o[slot], d = A.ray_d[slot];
-    r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
-  }
-  // ---- closest hit (main.cu:57) ----
-  const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
-  int q = -1;
-  if (active) {
-    A.hit[slot] = make_float2(h.t, __int_as_float(h.tlp < 0 ? -1 : (h.tlp | (h.face << 28))));
-    q = h.tlp < 0 ? (int)Q_MISS : S.tlp[h.tlp].queue;
-  }
-  // ---- bin by material class: per-warp counts per class in shared memory, ONE global atomic per class per block ----
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane < Q_COUNT) s_q[warp][lane] = 0;
+  // ---- bin the range by material class: ONE atomic per class per warp, positions by ballot ----
   __syncwarp();
-  const unsigned peers = __match_any_sync(0xFFFFFFFFu, q);
-  if (q >= 0 && lane == __ffs(peers) - 1) s_q[warp][q] = __popc(peers);
-  __syncthreads();
-  if (threadIdx.x < Q_COUNT) {
-    int tot = 0;
+  int qk[RT_RANGE_K];
+  int mycnt = 0;  // lane c < Q_COUNT: rays of class c in this range
 #pragma unroll
-    for (int w = 0; w < RT_TWARPS; ++w) { const int c = s_q[w][threadIdx.x]; s_q[w][threadIdx.x] = tot; tot += c; }
-    s_qbase[threadIdx.x] = tot > 0 ? atomicAdd(&C->n_queue[parity][threadIdx.x], tot) : 0;
+  for (int k = 0; k < RT_RANGE_K; ++k) {
+    const int g = base + 32 * k + lane;
+    int q = -1;
+    if (g < end) {
+      const int packed = __float_as_int(hit[g].y);
+      if (packed != RT_HIT_HOLE) q = packed < 0 ? (int)Q_MISS : ((packed >> 28) & 7);
+    }
+    qk[k] = q;
+#pragma unroll
+    for (int c = 0; c < Q_COUNT; ++c) {
+      const int n = __popc(__ballot_sync(0xFFFFFFFFu, q == c));
+      if (lane == c) mycnt += n;
+    }
   }
-  __syncthreads();
-  if (q >= 0) queues[(size_t)q * P.n_slots + s_qbase[q] + s_q[warp][q] + __popc(peers & ((1u << lane) - 1u))] = slot;
+  const int sub = wid & (RT_NSUB - 1);
+  int mybase = 0;
+  if (lane < Q_COUNT && mycnt > 0) mybase = atomicAdd(&C->n_queue[parity][lane * RT_NSUB + sub], mycnt);
+#pragma unroll
+  for (int c = 0; c < Q_COUNT; ++c) {
+    int off = __shfl_sync(0xFFFFFFFFu, mybase, c);
+    int* qp = queues + (size_t)(c * RT_NSUB + sub) * subcap;
+#pragma unroll
+    for (int k = 0; k < RT_RANGE_K; ++k) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, qk[k] == c);
+      if (qk[k] == c) qp[off + __popc(m & lt)] = base + 32 * k + lane;
+      off += __popc(m);
+    }
+  }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, RenderParams P, PathArrays A, const int* __restrict__ queues,
-                                                                   WaveCounters* C, int parity) {
-  // thread -> (queue, position): queues are laid end to end, each padded to a whole warp
-  int cnt[Q_COUNT];
-  int total = 0, rays = 0;
-#pragma unroll
-  for (int k = 0; k < Q_COUNT; ++k) { cnt[k] = C->n_queue[parity][k]; total += (cnt[k] + 31) & ~31; rays += cnt[k]; }
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, RenderParams P, PathArrays A, WaveCounters* C, int parity) {
+  const int lane = threadIdx.x & 31;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  const int wstart = gid - lane;
+  // warp -> (queue, position): the queues are laid end to end, each padded to a whole warp; one warp scan finds the warp's queue
+  const int cnt = lane < RT_NQ ? C->n_queue[parity][lane] : 0;
+  const int padded = (cnt + 31) & ~31;
+  int incl = padded;
 #pragma unroll
-    for (int k = 0; k < Q_COUNT; ++k) C->n_queue[parity ^ 1][k] = 0;  // next wave's trace fills these
-    C->rays += (unsigned long long)rays;
-    C->order_len = total;  // the next k_trace walks this wave's queue layout
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+  const int excl = incl - padded;
+  const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const int rays = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane < RT_NQ) C->n_queue[parity ^ 1][lane] = 0;  // the next wave's trace fills these
+    if (lane == 0) { C->rays += (unsigned long long)rays; C->order_len = total; }  // the next k_trace walks this wave's layout
   }
-  if (gid >= total) return;
-  int q = 0, base = 0, qcount = cnt[0];
-#pragma unroll
-  for (int k = 0; k < Q_COUNT - 1; ++k) {
-    const int padded = (cnt[k] + 31) & ~31;
-    if (q == k && gid >= base + padded) { base += padded; q = k + 1; qcount = cnt[k + 1]; }
-  }
-  const int pos = gid - base;
-  if (pos >= qcount) { A.order[gid] = -1; return; }  // warp padding between two queues
-  const int slot = queues[(size_t)q * P.n_slots + pos];
-  A.order[gid] = slot;
-  const float4 o = A.ray_o[slot], d = A.ray_d[slot];
-  const float4 thr4 = A.thr[slot], rad4 = A.rad[slot];
-  const SlotInfo si = pixel_info(P, __float_as_int(d.w));
-  Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
-  V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(rad4.x, rad4.y, rad4.z);
-  int bounce = __float_as_int(thr4.w);
-  const int sample = __float_as_int(rad4.w);
+  if (wstart >= total) return;
+  const unsigned mq = __ballot_sync(0xFFFFFFFFu, lane < RT_NQ && excl <= wstart);
+  const int qi = 31 - __clz(mq);
+  const int qbase = __shfl_sync(0xFFFFFFFFu, excl, qi), qcount = __shfl_sync(0xFFFFFFFFu, cnt, qi);
+  const int q = qi / RT_NSUB;  // material class: warp-uniform
+  const int pos = gid - qbase;
+  const bool live = pos < qcount;  // else: warp padding between two queues
+  const int po = parity ^ 1;
+  bool need = false;     // the sample ended: take the next one
   typename RngOf<MODE>::type g;
-  rng_load<MODE>(g, A, P, slot, si.pix, sample, bounce + 1);
-  bool sample_done;
-  Ray next; next.o = r.o; next.d = r.d; next.tm = r.tm;
-  if (q == Q_MISS) {
-    // main.cu:58-68
-    V3 bg = P.background;
-    if (P.gradient) {
-      const float uy = fdiv(r.d.y, vlen(r.d));
-      const float t = fmul(0.5f, fadd(uy, 1.0f));
-      const float omt = fsub(1.0f, t);
-      bg = v3(ffma(t, 0.5f, omt), ffma(t, 0.7f, omt), fadd(t, omt));
-    }
-    rad = v3(ffma(thr.x, bg.x, rad.x), ffma(thr.y, bg.y, rad.y), ffma(thr.z, bg.z, rad.z));
-    sample_done = true;
-  } else {
-    const float2 hh = A.hit[slot];
-    const int packed = __float_as_int(hh.y);
-    const int tlp = packed & 0x0FFFFFFF, face = packed >> 28;
-    const DTlp T = S.tlp[tlp];
-    const DMat m = S.mats[T.mat];
-    Rec rec;
-    if (ref_type(T.ref) == G_MEDIUM) {  // constant_medium.cuh:58-62
-      rec.t = hh.x;
-      rec.p = vmad(hh.x, r.d, r.o);
-      rec.n = v3(1, 0, 0);
-      rec.u = rec.v = 0.f;
-    } else {
-      geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec, face);
-    }
-    if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
-      const V3 e = material_emitted(S, m, rec);
-      rad = v3(ffma(thr.x, e.x, rad.x), ffma(thr.y, e.y, rad.y), ffma(thr.z, e.z, rad.z));
-    }
-    V3 att;
-    const bool scattered = material_scatter(S, m, r, rec, g, att, next);  // main.cu:76
-    if (scattered) {
-      thr = vmul(thr, att);  // main.cu:82
-      ++bounce;
-    }
-    sample_done = !scattered || bounce >= P.max_depth;
+  int lpix = 0, sample = 0;
+  // Miss and light warps end every sample they hold (main.cu:58-68; lights do not scatter, material.cuh:174-178): their
+  // next work items are reserved NOW, so that the round trip of the atomic overlaps the state loads (taken after the
+  // shading it was 19% of k_shade's stall samples).
+  const bool early = MODE == RNG_PHILOX && (q == Q_MISS || q == Q_LIGHT);
+  unsigned long long w_early = 0;
+  if (early) {
+    const unsigned mlive = __ballot_sync(0xFFFFFFFFu, live);
+    const int leader = __ffs(mlive) - 1;
+    if (lane == leader) w_early = atomicAdd(A.next_work, (unsigned long long)__popc(mlive));
+    w_early = __shfl_sync(0xFFFFFFFFu, w_early, leader) + (unsigned long long)__popc(mlive & ((1u << lane) - 1u));
   }
-  if (sample_done) {
-    if constexpr (MODE == RNG_REFERENCE) {
-      // render: col += color(...) (main.cu:124)
-      float4 c = A.col[slot];
-      c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
-      A.col[slot] = c;
+  if (live) {
+    const int idx = A.queues[(size_t)qi * A.subcap + pos];
+    const float4 o = A.ray_o[parity][idx], d = A.ray_d[parity][idx];
+    const float4 thr4 = A.thr[parity][idx], rad4 = A.rad[parity][idx];
+    const float2 hh = A.hit[idx];
+    lpix = __float_as_int(d.w);
+    const SlotInfo si = pixel_info(P, lpix);
+    Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+    V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(rad4.x, rad4.y, rad4.z);
+    int bounce = __float_as_int(thr4.w);
+    sample = __float_as_int(rad4.w);
+    rng_load(g, A, P, lpix, si.pix, sample, bounce + 1);
+    bool sample_done;
+    Ray nxt; nxt.o = r.o; nxt.d = r.d; nxt.tm = r.tm;
+    if (q == Q_MISS) {
+      // main.cu:58-68
+      V3 bg = P.background;
+      if (P.gradient) {
+        const float uy = fdiv(r.d.y, vlen(r.d));
+        const float t = fmul(0.5f, fadd(uy, 1.0f));
+        const float omt = fsub(1.0f, t);
+        bg = v3(ffma(t, 0.5f, omt), ffma(t, 0.7f, omt), fadd(t, omt));
+      }
+      rad = v3(ffma(thr.x, bg.x, rad.x), ffma(thr.y, bg.y, rad.y), ffma(thr.z, bg.z, rad.z));
+      sample_done = true;
     } else {
-      if (isfinite(rad.x) && isfinite(rad.y) && isfinite(rad.z)) {
-        unsigned long long* acc = A.acc64 + 3 * (size_t)si.lpix;
-        fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
+      const int packed = __float_as_int(hh.y);
+      const int tlp = packed & (int)RT_TLP_MASK, face = (packed >> 25) & 7;
+      const DTlp T = S.tlp[tlp];
+      const DMat m = S.mats[T.mat];
+      Rec rec;
+      if (ref_type(T.ref) == G_MEDIUM) {  // constant_medium.cuh:58-62
+        rec.t = hh.x;
+        rec.p = vmad(hh.x, r.d, r.o);
+        rec.n = v3(1, 0, 0);
+        rec.u = rec.v = 0.f;
       } else {
-        atomicAdd(&C->nonfinite, 1u);
+        geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec, face);
+      }
+      if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
+        const V3 e = material_emitted(S, m, rec);
+        rad = v3(ffma(thr.x, e.x, rad.x), ffma(thr.y, e.y, rad.y), ffma(thr.z, e.z, rad.z));
+      }
+      V3 att;
+      const bool scattered = material_scatter(S, m, r, rec, g, att, nxt);  // main.cu:76
+      if (scattered) {
+        thr = vmul(thr, att);  // main.cu:82
+        ++bounce;
+      }
+      sample_done = !scattered || bounce >= P.max_depth;
+    }
+    if (sample_done) {
+      if constexpr (MODE == RNG_REFERENCE) {
+        // render: col += color(...) (main.cu:124)
+        float4 c = A.col[lpix];
+        c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
+        A.col[lpix] = c;
+      } else {
+        // non-finite samples (and samples too large for the fixed-point sum) are dropped and counted
+        if (fabsf(rad.x) < RT_FIXED_MAX && fabsf(rad.y) < RT_FIXED_MAX && fabsf(rad.z) < RT_FIXED_MAX) {
+          unsigned long long* acc = A.acc64 + 3 * (size_t)lpix;
+          fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
+        } else {
+          atomicAdd(&C->nonfinite, 1u);
+        }
+      }
+      need = true;
+    } else {
+      A.ray_o[po][gid] = make_float4(nxt.o.x, nxt.o.y, nxt.o.z, nxt.tm);
+      A.ray_d[po][gid] = make_float4(nxt.d.x, nxt.d.y, nxt.d.z, d.w);
+      A.thr[po][gid] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce));
+      A.rad[po][gid] = make_float4(rad.x, rad.y, rad.z, rad4.w);
+    }
+  } else {
+    write_hole(A, po, gid);
+  }
+  // ---- path regeneration (main.cu:119-123): a lane whose sample has ended takes the next one ----
+  if constexpr (MODE == RNG_PHILOX) {
+    const unsigned mneed = __ballot_sync(0xFFFFFFFFu, need);
+    if (mneed) {
+      unsigned long long w = w_early;
+      if (!early) {
+        const int leader = __ffs(mneed) - 1;
+        if (lane == leader) w = atomicAdd(A.next_work, (unsigned long long)__popc(mneed));  // one atomic per warp
+        w = __shfl_sync(0xFFFFFFFFu, w, leader) + (unsigned long long)__popc(mneed & ((1u << lane) - 1u));
+      }
+      if (need) {
+        if (w < (unsigned long long)P.work_total) {
+          work_to_pixel_sample(P, w, lpix, sample);
+          const SlotInfo si = pixel_info(P, lpix);
+          rng_load(g, A, P, lpix, si.pix, sample, 0);
+          start_sample(S, P, A, po, gid, si, sample, g);
+        } else {
+          write_hole(A, po, gid);
+        }
       }
     }
-    A.thr[slot].w = __int_as_float((int)SLOT_NEEDS_SAMPLE);  // k_trace of the next wave regenerates the slot
   } else {
-    A.ray_o[slot] = make_float4(next.o.x, next.o.y, next.o.z, next.tm);
-    A.ray_d[slot] = make_float4(next.d.x, next.d.y, next.d.z, d.w);
-    A.thr[slot] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce));
-    A.rad[slot] = make_float4(rad.x, rad.y, rad.z, rad4.w);
+    if (need) {
+      if (sample + 1 < P.sample_base + P.sample_count) {
+        const SlotInfo si = pixel_info(P, lpix);
+        start_sample(S, P, A, po, gid, si, sample + 1, g);  // the pixel's stream carries on
+      } else {
+        write_hole(A, po, gid);
+      }
+    }
+    if (live) rng_store(g, A, P, lpix);
   }
-  rng_store(g, A, P, slot);
 }
 
 RT_D float apply_gamma(float c, float gamma) {  // main.cu:37-42
@@ -421,8 +486,8 @@ __global__ void k_aov(DScene S, RenderParams P, int* obj, int* mat, float* tout,
   }
   const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
   if (!active) return;
-  obj[lpix] = h.tlp;
-  mat[lpix] = h.tlp >= 0 ? S.tlp[h.tlp].mat : -1;
+  obj[lpix] = h.tlp >= 0 ? tlp_index(h.tlp) : -1;
+  mat[lpix] = h.tlp >= 0 ? S.tlp[tlp_index(h.tlp)].mat : -1;
   tout[lpix] = h.tlp >= 0 ? h.t : 0.f;
 }
 

@@ -93,6 +93,7 @@ struct DScene {
   const DSphere* spheres; const DQuad* quads; const DXform* xforms; const DMedium* media;
   const DMat* mats; const DTex* texs; const DImage* images;
   const DTlp* tlp; const BVH4Node* nodes;
+  const float4* qplanes;      // (normal, D) of quads[i], contiguous: a box test reads its six planes from 96 consecutive bytes
   int n_tlp, n_nodes;
   DCamera cam;
 };
