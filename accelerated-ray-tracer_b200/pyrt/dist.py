@@ -66,29 +66,14 @@ def init_process_group(backend=None):
     return world, rank, local
 
 
-_staging = {}
-
-
 def reduce_sum_to_root(t, root=0):
-    """Spp split: sum the ranks' linear-radiance buffers into rank `root` (in place there).
-    CUDA tensors go through a persistent staging tensor of the same size (one D2D copy each way, ~8 MB): the
-    library's buffers are plain cudaMalloc memory that changes with every scene, and NCCL pays a one-off setup
-    cost per new buffer address that would otherwise land inside every step."""
-    import torch
+    """Spp split: sum the ranks' linear-radiance buffers into rank `root`, IN PLACE on the library's accumulation
+    buffer (rt_accum_device_ptr: one allocation per scene, recycled through the library's block cache, so NCCL sees
+    the same few addresses step after step - no staging copies)."""
     import torch.distributed as dist
     if not (dist.is_initialized() and dist.get_world_size() > 1):
         return t
-    if t.is_cuda:
-        key = (t.device, t.numel(), t.dtype)
-        st = _staging.get(key)
-        if st is None:
-            st = _staging[key] = torch.empty_like(t)
-        st.copy_(t)
-        dist.reduce(st, dst=root, op=dist.ReduceOp.SUM)
-        if dist.get_rank() == root:
-            t.copy_(st)
-    else:
-        dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
+    dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
     return t
 
 

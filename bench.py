@@ -6,10 +6,15 @@ Book-2 final scene (create_world_final, main.cu:498-562) at 800x800, on N B200s 
   python bench.py --impl reference ...      the reference's own render code on the box's host cores
 
 A *step* is one progressive pass of --spp-per-step samples per pixel (default 1000) over the whole
-800x800 image on every GPU; steps use disjoint sample numbers, so the default K = 10 steps ARE the
-reference's 10000-spp final_scene() (main.cu:1179) at N = 1. At N > 1 every GPU renders its own
---spp-per-step share per step (weak scaling: per-GPU work fixed, N x the samples per step) and the
-linear-radiance sums are reduced to rank 0 with one NCCL reduce per step, inside the timed region.
+800x800 image; steps use disjoint sample numbers, so the default K = 10 steps ARE the reference's
+10000-spp final_scene() (main.cu:1179). At N > 1 the SAME job is split N ways (strong scaling, the
+shape BASELINE.json configs[3] names: a fixed 800x800 x 10000-spp render tile/spp-split across 1/2/4/8
+GPUs): --split spp (default) gives every GPU 1/N of the pass's sample numbers and sums the
+linear-radiance buffers on rank 0 with one NCCL reduce per step; --split tile gives every GPU its
+interleaved scanlines and gathers them. Both exchanges are inside the timed region. --scaling weak
+keeps the per-GPU work fixed instead (every GPU renders --spp-per-step samples per step). After the
+timed region rank 0 renders the last step's sample set alone and compares it with the image the N
+ranks produced ("parity_check": tile split bit-identical, spp split to float-sum rounding).
 
 value    whole-job Mrays/s with the scene resident in HBM: rays of all ranks / (max-over-ranks CUDA-event
          span of the K steps, barrier + synchronize on both sides).
@@ -186,7 +191,7 @@ def reference_arm(args):
     sample = "%dx%d x %d spp per step (of the 10000-spp config; throughput is linear in spp)" % (NX, NY, ns)
     line = {"metric": METRIC, "value": round(v, 4), "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / max(len(res), 1), 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Book-2 final scene (create_world_final) 800x800, depth 50; " + sample,
                        "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": ns},
             "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
@@ -224,6 +229,10 @@ def main():
                     help="N > 1: spp split (default: every GPU renders all pixels for its own --spp-per-step samples, one NCCL "
                          "reduce per step) or tile split (every GPU renders its interleaved scanlines for N x --spp-per-step "
                          "samples, one NCCL gather per step); per-GPU work is the same in both")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong (default) = the fixed 800x800 x spp-per-step pass split N ways; weak = every GPU "
+                         "renders spp-per-step samples per step")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -258,24 +267,36 @@ def main():
         torch.cuda.synchronize()
 
     sc = pyrt.Scene(SCENE_ID, NX, NY, texture_dir=tex, device=local)
-    passes = (W + K) * world  # every (step, rank) renders a disjoint block of S sample numbers
-    spp_all = S * passes
+    weak = args.scaling == "weak" and world > 1
+    S_step = S * world if weak else S          # samples per pixel of one step, all ranks together
+    n_steps_all = W + K + 1                     # warm-up + timed + the profiled / parity step
+    spp_all = S_step * n_steps_all
+    tile = args.split == "tile" and world > 1
 
-    def step(i, profile=False):
-        if args.split == "tile" and world > 1:
-            # tile split: rank r owns scanlines j = r (mod N) and renders N x S samples for them; a different seed per step
-            st = sc.render(spp=S * world, rng_mode=0, split_mode=0, rank=rank, world=world, seed=1984 + i, profile=profile)
-            rdist.gather_rows_to_root(rdist.fb_tensor(sc).view(st.rows_local, st.nx, 3), NY)  # NCCL gather: the image on rank 0
+    def step(i, profile=False, alone=False):
+        """Step i renders sample numbers [i * S_step, (i + 1) * S_step) of every pixel, split over the ranks
+        (alone: this rank renders the whole step by itself - the parity check)."""
+        w_, r_ = (1, 0) if alone else (world, rank)
+        if tile and not alone:
+            # tile split: rank r owns scanlines j = r (mod N) and renders all S_step samples of step i for them
+            st = sc.render(spp=S_step, rng_mode=0, split_mode=0, rank=r_, world=w_, seed=1984 + i, profile=profile)
+            full = rdist.gather_rows_to_root(rdist.fb_tensor(sc).view(st.rows_local, st.nx, 3), NY)  # NCCL gather: the image on rank 0
             torch.cuda.current_stream().synchronize()
-            return st
-        st = sc.render(spp=spp_all, rng_mode=0, split_mode=1, rank=i * world + rank, world=passes, profile=profile)
-        if world > 1:
-            rdist.reduce_sum_to_root(rdist.accum_tensor(sc))  # NCCL reduce over NVLink: the image of this pass on rank 0
+            return st, full
+        if tile:
+            st = sc.render(spp=S_step, rng_mode=0, split_mode=0, rank=0, world=1, seed=1984 + i, profile=profile)
+            return st, rdist.fb_tensor(sc).view(st.rows_local, st.nx, 3)
+        # spp split: the pass's sample numbers are cut into world contiguous shares
+        st = sc.render(spp=spp_all, rng_mode=0, split_mode=1, rank=i * w_ + r_, world=n_steps_all * w_, profile=profile)
+        acc = rdist.accum_tensor(sc)
+        if w_ > 1:
+            rdist.reduce_sum_to_root(acc)  # NCCL reduce over NVLink, in place on the library's accumulation buffer
             torch.cuda.current_stream().synchronize()  # the next pass overwrites the accumulation buffer
-        return st
+        return st, acc
 
     for i in range(W):
         step(i)
+    result = None
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
@@ -287,7 +308,7 @@ def main():
     trace_ms = shade_ms = 0.0
     waves = 0
     for i in range(W, W + K):
-        st = step(i, profile=args.profile_in_timed)
+        st, result = step(i, profile=args.profile_in_timed)
         rays += st.rays
         launches += st.kernel_launches
         kernel_ms += st.device_ms
@@ -299,8 +320,28 @@ def main():
     ck = clocks.stop()
     span_ms = e0.elapsed_time(e1)
     prof_rays = rays
+    # ---- parity of the multi-GPU result: rank 0 renders the last timed step's samples alone ----
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        got = result.clone() if rank == 0 else None
+        barrier()
+        if rank == 0:
+            _, want = step(W + K - 1, alone=True)
+            torch.cuda.synchronize()
+            a, b = got.float().flatten(), want.float().flatten()
+            diff = (a - b).abs()
+            if tile:
+                ok = bool(torch.equal(a, b))
+                parity = {"ok": ok, "split": "tile", "rule": "bit-identical to the 1-rank render of the same samples",
+                          "pixels_differing": int((diff.view(-1, 3) > 0).any(dim=1).sum())}
+            else:
+                tol = 2e-6 * b.abs() + 1e-6
+                ok = bool((diff <= tol).all())
+                parity = {"ok": ok, "split": "spp", "rule": "|sum_N - sum_1| <= 2e-6*|sum_1| + 1e-6 per channel (float add order)",
+                          "max_abs_diff": float(diff.max()), "max_rel_diff": float((diff / (b.abs() + 1e-6)).max())}
+        barrier()
     if not args.profile_in_timed:  # one extra (untimed) profiled step for the per-kernel durations
-        st = step(W + K - 1, profile=True)
+        st, _ = step(W + K, profile=True, alone=True)
         trace_ms, shade_ms, waves, prof_rays = st.trace_ms, st.shade_ms, st.profiled_waves, st.rays
     t = torch.tensor([span_ms, float(rays), float(launches), kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -312,7 +353,7 @@ def main():
     else:
         rays_all, launches_all = float(rays), launches
     value = rays_all / span_ms / 1e3
-    samples_all = float(NX) * NY * S * K * world
+    samples_all = float(NX) * NY * S_step * K
 
     # ---- e2e: C ABI with host buffers, every step builds, renders, reads back ----
     e2e = None
@@ -328,13 +369,13 @@ def main():
             ta = time.perf_counter()
             s2 = pyrt.Scene(SCENE_ID, NX, NY, texture_dir=tex, device=local)
             tb = time.perf_counter()
-            st = s2.render(spp=spp_all, rng_mode=0, split_mode=1, rank=(W + i) * world + rank, world=passes)
+            st = s2.render(spp=spp_all, rng_mode=0, split_mode=1, rank=(W + i) * world + rank, world=n_steps_all * world)
             tc = time.perf_counter()
             if world > 1:
                 rdist.reduce_sum_to_root(rdist.accum_tensor(s2))
                 torch.cuda.synchronize()
             if rank == 0:
-                s2.resolve(total_spp=S * world)
+                s2.resolve(total_spp=S_step)
                 pyrt._check(pyrt.lib().rt_readback(s2._h, host_fb.ctypes.data, None, None))
                 d2h += host_fb.nbytes
             td = time.perf_counter()
@@ -370,11 +411,13 @@ def main():
         tpr, tsrc = ncu_traffic_per_ray()
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": round(span_ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(span_ms / K, 3), "higher_is_better": True, "scaling": "weak" if weak else "strong",
+            "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Book-2 final scene (create_world_final + earthmap) 800x800, depth 50, %d spp per step "
-                                   "per GPU; default 10 steps = the 10000-spp config" % S,
-                       "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": S, "spp_total": S * K * world,
+                                   "%s; default 10 steps = the 10000-spp config" %
+                                   (S_step, "(%d per GPU)" % S if weak else "split over the %d GPU(s)" % world),
+                       "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": S_step, "spp_total": S_step * K,
                        "max_depth": 50, "rng": "philox4x32-10", "parallelism": "%s-split x%d, scene replicated" % (args.split if world > 1 else "spp", world),
                        "l2": "inputs larger than L2: %.0f MB of path state (%d slots x 88 B) streamed every wave" %
                              (st.n_slots * 88 / 1e6, st.n_slots)},
@@ -383,6 +426,7 @@ def main():
             "kernel_ms_per_step": round(kernel_ms / K, 3),
             "gpu_launches": launches_all,
             "clocks": ck,
+            "parity_check": parity,
             "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 1) if achieved else None,
                          "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4) if achieved else None,
