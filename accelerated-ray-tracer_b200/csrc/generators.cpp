@@ -306,10 +306,15 @@ std::string generate_scene(SceneDesc& sd, DevMath& dm, int scene_id, int nx, int
   SceneBuilder B(sd, dm);
   auto load = [&](const char* name, int& id) -> std::string {
     HostImage im;
-    // The reference opens textures/<name>.jpg relative to the CWD (main.cu:1186); this build takes the
-    // decoded pixels as binary PPM (P6) <name>.ppm in texture_dir.
-    std::string p = (texture_dir.empty() ? std::string("textures") : texture_dir) + "/" + name + ".ppm";
-    if (!load_ppm(p, im)) return "cannot load texture " + p;
+    // The reference opens textures/<name>.jpg relative to the CWD (main.cu:1186, image_io.h:24-41): <name>.jpg in
+    // texture_dir is decoded here (jpeg_baseline.cpp: the same bytes as the reference's decoder); a pre-decoded binary
+    // PPM (P6) <name>.ppm is taken when there is no .jpg.
+    const std::string dir = texture_dir.empty() ? std::string("textures") : texture_dir;
+    std::string e = load_texture_file(dir + "/" + name + ".jpg", im);
+    if (!e.empty()) {
+      const std::string e2 = load_texture_file(dir + "/" + name + ".ppm", im);
+      if (!e2.empty()) return "cannot load texture: " + e + "; " + e2;
+    }
     id = B.add_image(im);
     return "";
   };

@@ -827,6 +827,20 @@ extern "C" int rt_resolve(rt_scene* s, int32_t total_spp, float gamma) {
   return 0;
 }
 
+extern "C" int rt_load_texture(const char* path, unsigned char* rgb, size_t cap, int32_t* w, int32_t* h) {
+  if (!path || !w || !h) return fail("rt_load_texture: null argument");
+  HostImage im;
+  try {
+    const std::string err = load_texture_file(path, im);
+    if (!err.empty()) return fail("rt_load_texture: " + err);
+  } catch (const std::exception& e) {
+    return fail(std::string("rt_load_texture: ") + e.what());
+  }
+  *w = im.width; *h = im.height;
+  if (rgb && cap >= im.px.size()) memcpy(rgb, im.px.data(), im.px.size());
+  return 0;
+}
+
 extern "C" long rt_write_ppm(const char* path, const float* rgb, int32_t nx, int32_t ny, int32_t double_scale) {
   if (!rgb || nx <= 0 || ny <= 0) { fail("rt_write_ppm: bad argument"); return -1; }
   FILE* f = path ? fopen(path, "w") : stdout;

@@ -329,6 +329,18 @@ bool load_ppm(const std::string& path, HostImage& out) {
   return got == out.px.size();
 }
 
+std::string load_texture_file(const std::string& path, HostImage& out) {
+  const size_t dot = path.rfind('.');
+  std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
+  for (auto& c : ext) c = (char)tolower((unsigned char)c);
+  if (ext == "jpg" || ext == "jpeg") {
+    std::string err;
+    return load_jpeg(path, out, err) ? "" : err;
+  }
+  if (ext == "ppm") return load_ppm(path, out) ? "" : "cannot read " + path + " (binary PPM, P6, maxval 255)";
+  return path + ": unknown texture format (expected .jpg or .ppm)";
+}
+
 std::string sd_serialize(const SceneDesc& sd) {
   rt_sd_header h;
   memset(&h, 0, sizeof(h));

@@ -117,6 +117,9 @@ std::string generate_scene(SceneDesc& sd, DevMath& dm, int scene_id, int nx, int
 std::vector<int> reference_leaf_order(const SceneDesc& sd, int limit = 20000);
 
 bool load_ppm(const std::string& path, HostImage& out);
+bool load_jpeg(const std::string& path, HostImage& out, std::string& err);  // jpeg_baseline.cpp
+// .jpg / .jpeg (baseline JPEG, decoded like the reference's stbi_load(path, .., 3)) or .ppm (P6). "" or an error message.
+std::string load_texture_file(const std::string& path, HostImage& out);
 std::string sd_serialize(const SceneDesc& sd);  // binary SD file image
 std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* const* images, int n_images, SceneDesc& sd);  // "" or an error
 

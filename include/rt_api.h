@@ -115,6 +115,11 @@ int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
  * same device (cudaMalloc/cudaFree of the ~0.4 GB path state cost more than a scene build); this releases them. */
 void rt_trim_device_cache(void);
 
+/* Host-only: decodes an image texture file the way rt_build_scene does - <name>.jpg (baseline JPEG; the bytes equal
+ * what the reference's stbi_load(path, &w, &h, &n, 3) returns, image_io.h:24-41) or binary <name>.ppm - to 8-bit RGB.
+ * *w / *h receive the size; pixels are copied if cap >= w*h*3 (call with rgb = NULL to query the size). */
+int rt_load_texture(const char* path, unsigned char* rgb, size_t cap, int32_t* w, int32_t* h);
+
 /* PPM writer of the scene functions (main.cu:1212-1221): "P3\n{nx} {ny}\n255\n", rows j = ny-1..0,
  * int(255.99f*c) per channel, no clamp. rgb is a FULL image (ny*nx*3, row 0 = bottom). double_scale != 0
  * reproduces bouncing_spheres' `int(255.99*c)` in double (main.cu:722-724). Returns bytes written or < 0. */

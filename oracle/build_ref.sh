@@ -31,6 +31,11 @@ if [ "$WHAT" = all ] || [ "$WHAT" = cpu ]; then
   for t in earthmap poolball porcelain 8ball; do
     "$ROOT/oracle/_ref/ref_cpu" --decode "$REF/textures/$t.jpg" "$ROOT/oracle/_ref/textures/$t.ppm"
   done
+  "$ROOT/oracle/_ref/ref_cpu" --decode "$REF/textures/hardwood.jpg" "$ROOT/oracle/_ref/textures/hardwood.ppm"
+  # the reference's own .jpg files next to what ITS decoder makes of them: input and expected output of the product's
+  # JPEG decoder test (oracle/_ref is git-ignored; it travels to the GPU box like the other built files)
+  mkdir -p "$ROOT/oracle/_ref/textures_jpg"
+  cp "$REF"/textures/*.jpg "$ROOT/oracle/_ref/textures_jpg/"
   echo "built oracle/_ref/ref_cpu + textures"
 fi
 if [ "$WHAT" = all ] || [ "$WHAT" = gpu ]; then

@@ -247,6 +247,21 @@ def test_scale_up_c5_bvh_matches_brute_force_ids(pyrt, built):
     assert np.array_equal(o_t.view(np.uint32), t.view(np.uint32))
 
 
+def test_scene_reads_the_references_jpg_textures(pyrt):
+    """rt_build_scene opens textures/<name>.jpg like the reference's scene functions (main.cu:816, 1186): a texture directory
+    holding only the reference's .jpg files renders the same bits as the directory of reference-decoded PPMs."""
+    root = os.path.dirname(os.path.dirname(__file__))
+    jdir, pdir = os.path.join(root, "oracle", "_ref", "textures_jpg"), os.path.join(root, "oracle", "_ref", "textures")
+    if not (os.path.exists(os.path.join(jdir, "earthmap.jpg")) and os.path.exists(os.path.join(pdir, "earthmap.ppm"))):
+        pytest.skip("oracle/_ref textures not built")
+    out = []
+    for d in (jdir, pdir):
+        with pyrt.Scene(3, 200, 100, texture_dir=d) as sc:
+            sc.render(spp=4, rng_mode=1)
+            out.append(sc.framebuffer())
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
+
+
 def test_cli_ppm_on_stdout_matches_reference_image(pyrt, golden, built):
     """rt_cli = the reference's main(): P3 PPM on stdout, diagnostics on stderr, exit code 99 on a library error.
     C1 in reference-RNG mode must print exactly the integers the reference prints (main.cu:715-727, double 255.99)."""

@@ -48,6 +48,52 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rt_scene
     assert sizes[4:] == [pyrt.TEX_DT.itemsize, pyrt.MAT_DT.itemsize, pyrt.OBJ_DT.itemsize, pyrt.CAM_DT.itemsize, pyrt.HDR_DT.itemsize]
 
 
+JPEG_DIR = os.path.join(ROOT, "oracle", "_ref", "textures_jpg")
+PPM_DIR = os.path.join(ROOT, "oracle", "_ref", "textures")
+
+
+@pytest.mark.parametrize("name", ["earthmap", "poolball", "porcelain", "8ball", "hardwood"])
+def test_jpeg_decoder_gives_the_reference_decoders_bytes(pyrt, name):
+    """The product decodes textures/<name>.jpg itself (csrc/jpeg_baseline.cpp) where the reference calls stbi_load
+    (image_io.h:24-41). Texels enter the render bit for bit, so the decode must equal the reference decoder's output byte
+    for byte: oracle/_ref/textures/<name>.ppm is what the reference's own decoder (compiled into oracle/_ref/ref_cpu)
+    made of the same file. Covers 4:4:4 (earthmap) and 4:2:0 (the others) baseline files, 1024x512 and 824x360."""
+    jpg, ppm = os.path.join(JPEG_DIR, name + ".jpg"), os.path.join(PPM_DIR, name + ".ppm")
+    if not (os.path.exists(jpg) and os.path.exists(ppm)):
+        pytest.skip("oracle/_ref textures not built (needs /root/reference once: oracle/build_ref.sh cpu)")
+    mine = pyrt.load_texture(jpg)
+    want = pyrt.load_texture(ppm)
+    assert mine.shape == want.shape and mine.shape[2] == 3
+    assert np.array_equal(mine, want), "%d bytes differ" % int((mine != want).sum())
+
+
+def test_jpeg_decoder_rejects_what_it_cannot_decode_exactly(pyrt, tmp_path):
+    with pytest.raises(pyrt.RtError, match="cannot open"):
+        pyrt.load_texture(str(tmp_path / "missing.jpg"))
+    (tmp_path / "junk.jpg").write_bytes(b"not a jpeg at all")
+    with pytest.raises(pyrt.RtError, match="not a JPEG"):
+        pyrt.load_texture(str(tmp_path / "junk.jpg"))
+    with pytest.raises(pyrt.RtError, match="unknown texture format"):
+        pyrt.load_texture(str(tmp_path / "x.png"))
+    jpg = os.path.join(JPEG_DIR, "poolball.jpg")
+    if os.path.exists(jpg):
+        raw = bytearray(open(jpg, "rb").read())
+        sof = raw.index(b"\xff\xc0")
+        prog = bytearray(raw); prog[sof + 1] = 0xC2  # a progressive frame header: refused, never decoded differently
+        (tmp_path / "prog.jpg").write_bytes(prog)
+        with pytest.raises(pyrt.RtError, match="progressive"):
+            pyrt.load_texture(str(tmp_path / "prog.jpg"))
+        (tmp_path / "cut.jpg").write_bytes(raw[: len(raw) // 3])  # truncated entropy data: decodes what is there or fails, no crash
+        try:
+            img = pyrt.load_texture(str(tmp_path / "cut.jpg"))
+            assert img.shape == (512, 1024, 3)
+        except pyrt.RtError:
+            pass
+        (tmp_path / "hdr.jpg").write_bytes(raw[: sof + 6])  # cut inside the frame header
+        with pytest.raises(pyrt.RtError):
+            pyrt.load_texture(str(tmp_path / "hdr.jpg"))
+
+
 def test_no_cpu_fallback(pyrt):
     """Without a CUDA device the render path must fail loudly, not fall back."""
     import torch
