@@ -13,7 +13,7 @@
 //     (9-3-3-1), rounding +8 >> 4 inside a row, +2 >> 2 at the row ends; h2v1 / h1v2 = the 1-D version;
 //   * YCbCr -> RGB in 20-bit fixed point with the constants rounded to 12 bits first.
 // tests/test_host.py checks the output against the PPMs that the reference's own decoder produced from the same files
-// (oracle/_ref/textures, made by `ref_cpu --decode`): byte-identical for all five textures.
+// (made once where the reference sources exist, by the checker-side harness): byte-identical for all five textures.
 // Progressive (SOF2), arithmetic-coded, 12-bit and CMYK files are rejected with an error: the reference's texture set
 // has none, and a silently different decode would break parity.
 #include <cstdint>

@@ -205,7 +205,7 @@ struct rt_scene {
   DBuf<WaveCounters> counters;          // one per slot pool
   DBuf<unsigned long long> next_work;
   WaveCounters* h_counters = nullptr;  // pinned, one per slot pool
-  DBuf<float> accum, fb, aov_t; DBuf<int> aov_obj, aov_mat; DBuf<unsigned long long> acc64;
+  DBuf<float> accum, fb, aov_t, reduce_tmp; DBuf<int> aov_obj, aov_mat; DBuf<unsigned long long> acc64;
   size_t slots_cap = 0, pix_cap = 0, accum_valid_pix = 0;
   RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
   ~rt_scene() {
@@ -387,13 +387,16 @@ static int upload_scene(rt_scene* s) {
     DBuf<int> left, right; DBuf<BuildBox> nbox; DBuf<int2> qa, qb;
     CU(left.alloc(n)); CU(right.alloc(n)); CU(nbox.alloc(2 * n)); CU(qa.alloc(n)); CU(qb.alloc(n));
     int root = 0;
-#ifdef RT_BVH_LBVH
+    // RT_BVH_BUILDER=lbvh: the plain radix tree over the Morton codes (Karras 2012) instead of PLOC - a different
+    // topology over the same leaves, kept for A/B runs and for the test that both return the same hits
+    const char* builder = getenv("RT_BVH_BUILDER");
+    if (builder && !strcmp(builder, "lbvh")) {
     DBuf<int> parent, flags;
     CU(parent.alloc(2 * n)); CU(flags.alloc(n));
     CU(cudaMemset(flags.p, 0, n * sizeof(int)));
     k_bvh_karras<<<G, B>>>(k_out.p, n, left.p, right.p, parent.p);
     k_bvh_fit<<<G, B>>>(d_boxes.p, v_out.p, n, left.p, right.p, parent.p, nbox.p, flags.p);
-#else
+    } else {
     // PLOC rounds: nearest neighbour search -> merge -> compaction, until one cluster (the root) is left
     DBuf<int> cl_a, cl_b, nn, next_id, d_m;
     CU(cl_a.alloc(n)); CU(cl_b.alloc(n)); CU(nn.alloc(n)); CU(next_id.alloc(1)); CU(d_m.alloc(1));
@@ -414,7 +417,7 @@ static int upload_scene(rt_scene* s) {
       m = m_new;
     }
     CU(cudaMemcpy(&root, cl_a.p, sizeof(int), cudaMemcpyDeviceToHost));
-#endif
+    }
     k_bvh_collapse<<<1, 1024>>>(n, root, left.p, right.p, nbox.p, v_out.p, s->tlp.p, s->nodes.p, d_nout.p, qa.p, qb.p);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -815,6 +818,48 @@ extern "C" int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats) {
   if (n_floats) *n_floats = (size_t)s->last.rows_local * s->last.nx * 3;
   return 0;
 }
+// ---- native multi-GPU exchange of the spp split (one process, one rt_scene per device) ----
+__global__ void k_accum_add(float* dst, const float* src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = fadd(dst[i], src[i]);
+}
+extern "C" int rt_accum_reduce(rt_scene* dst, rt_scene* const* src, int32_t n_src) {
+  if (!dst || (n_src > 0 && !src)) return fail("rt_accum_reduce: null argument");
+  CU(cudaSetDevice(dst->device));
+  const size_t n = (size_t)dst->last.rows_local * dst->last.nx * 3;
+  if (n == 0 || n_src <= 0) return 0;
+  const int G = (int)((n + 255) / 256);
+  for (int k = 0; k < n_src; ++k) {
+    rt_scene* o = src[k];
+    if (!o || o == dst) return fail("rt_accum_reduce: bad source scene");
+    if ((size_t)o->last.rows_local * o->last.nx * 3 != n || o->accum_valid_pix * 3 != n)
+      return fail("rt_accum_reduce: the scenes do not hold accumulation buffers of the same share (render all of them with the same "
+                  "resolution and split first)");
+    const float* from = o->accum.p;
+    if (o->device != dst->device) {
+      // peer memory over NVLink when the devices allow it: the add kernel loads the remote buffer directly (no staging
+      // copy); otherwise one cudaMemcpyPeerAsync into a buffer on dst's device
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, dst->device, o->device));
+      bool direct = false;
+      if (can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+        if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) direct = true;
+        cudaGetLastError();
+      }
+      if (!direct) {
+        if (dst->reduce_tmp.n < n) CU(dst->reduce_tmp.alloc(n));
+        CU(cudaMemcpyPeerAsync(dst->reduce_tmp.p, dst->device, o->accum.p, o->device, n * sizeof(float), dst->stream));
+        from = dst->reduce_tmp.p;
+      }
+    }
+    k_accum_add<<<G, 256, 0, dst->stream>>>(dst->accum.p, from, n);
+  }
+  CU(cudaStreamSynchronize(dst->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int rt_resolve(rt_scene* s, int32_t total_spp, float gamma) {
   if (!s) return fail("rt_resolve: null scene");
   CU(cudaSetDevice(s->device));
@@ -841,25 +886,89 @@ extern "C" int rt_load_texture(const char* path, unsigned char* rgb, size_t cap,
   return 0;
 }
 
-extern "C" long rt_write_ppm(const char* path, const float* rgb, int32_t nx, int32_t ny, int32_t double_scale) {
-  if (!rgb || nx <= 0 || ny <= 0) { fail("rt_write_ppm: bad argument"); return -1; }
-  FILE* f = path ? fopen(path, "w") : stdout;
-  if (!f) { fail("rt_write_ppm: cannot open output"); return -1; }
+// ---- image writers ----
+static int to_byte(float c, bool dbl) {  // the reference's int(255.99 * c) (float product; double for bouncing_spheres, main.cu:722-724)
+  return dbl ? int(255.99 * c) : int(255.99f * c);
+}
+static uint32_t crc32_of(const unsigned char* p, size_t n, uint32_t crc) {
+  static uint32_t table[256]; static bool init = false;
+  if (!init) { for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; } init = true; }
+  crc = ~crc;
+  for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}
+static void png_chunk(std::string& out, const char* type, const std::string& data) {
+  auto be32 = [&](uint32_t v) { char b[4] = {(char)(v >> 24), (char)(v >> 16), (char)(v >> 8), (char)v}; out.append(b, 4); };
+  be32((uint32_t)data.size());
+  std::string td = std::string(type, 4) + data;
+  out += td;
+  be32(crc32_of((const unsigned char*)td.data(), td.size(), 0));
+}
+
+// format 0: ASCII P3 exactly as the reference prints it (no clamp unless asked: main.cu:1212-1221 prints whatever
+// int(255.99*c) gives); 1: binary P6; 2: PNG (8-bit RGB, stored deflate blocks - no compression library needed).
+// P6 and PNG hold bytes, so they always clamp to [0, 255]. Rows are written top scanline first (j = ny-1..0).
+extern "C" long rt_write_image(const char* path, const float* rgb, int32_t nx, int32_t ny, int32_t format, int32_t clamp,
+                               int32_t double_scale) {
+  if (!rgb || nx <= 0 || ny <= 0 || format < 0 || format > 2) { fail("rt_write_image: bad argument"); return -1; }
+  const bool dbl = double_scale != 0, clip = clamp != 0 || format != 0;
+  auto chan = [&](float c) { int v = to_byte(c, dbl); if (clip) v = v < 0 ? 0 : v > 255 ? 255 : v; return v; };
   std::string out;
-  out.reserve((size_t)nx * ny * 12 + 32);
   char line[64];
-  snprintf(line, sizeof(line), "P3\n%d %d\n255\n", nx, ny);
-  out += line;
-  for (int j = ny - 1; j >= 0; j--)
-    for (int i = 0; i < nx; i++) {
-      const float* c = rgb + 3 * ((size_t)j * nx + i);
-      int ir, ig, ib;
-      if (double_scale) { ir = int(255.99 * c[0]); ig = int(255.99 * c[1]); ib = int(255.99 * c[2]); }
-      else { ir = int(255.99f * c[0]); ig = int(255.99f * c[1]); ib = int(255.99f * c[2]); }
-      snprintf(line, sizeof(line), "%d %d %d\n", ir, ig, ib);
-      out += line;
+  if (format == 0) {
+    out.reserve((size_t)nx * ny * 12 + 32);
+    snprintf(line, sizeof(line), "P3\n%d %d\n255\n", nx, ny);
+    out += line;
+    for (int j = ny - 1; j >= 0; j--)
+      for (int i = 0; i < nx; i++) {
+        const float* c = rgb + 3 * ((size_t)j * nx + i);
+        snprintf(line, sizeof(line), "%d %d %d\n", chan(c[0]), chan(c[1]), chan(c[2]));
+        out += line;
+      }
+  } else {
+    std::string raw;  // top row first; PNG rows carry a filter byte (0 = none)
+    raw.reserve(((size_t)nx * 3 + 1) * ny);
+    for (int j = ny - 1; j >= 0; j--) {
+      if (format == 2) raw.push_back(0);
+      for (int i = 0; i < nx; i++) {
+        const float* c = rgb + 3 * ((size_t)j * nx + i);
+        raw.push_back((char)chan(c[0])); raw.push_back((char)chan(c[1])); raw.push_back((char)chan(c[2]));
+      }
     }
-  size_t w = fwrite(out.data(), 1, out.size(), f);
+    if (format == 1) {
+      snprintf(line, sizeof(line), "P6\n%d %d\n255\n", nx, ny);
+      out = line + raw;
+    } else {
+      out.assign("\x89PNG\r\n\x1a\n", 8);
+      std::string ihdr(13, 0);
+      for (int k = 0; k < 4; ++k) { ihdr[k] = (char)((uint32_t)nx >> (24 - 8 * k)); ihdr[4 + k] = (char)((uint32_t)ny >> (24 - 8 * k)); }
+      ihdr[8] = 8; ihdr[9] = 2;  // 8 bits per channel, colour type 2 (RGB)
+      png_chunk(out, "IHDR", ihdr);
+      std::string z("\x78\x01", 2);  // zlib header, then stored (uncompressed) deflate blocks of <= 65535 bytes
+      uint32_t a1 = 1, a2 = 0;  // Adler-32 of the raw data
+      for (size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+        const size_t n = std::min<size_t>(65535, raw.size() - off);
+        const bool last = off + n >= raw.size();
+        const char hdr[5] = {(char)(last ? 1 : 0), (char)(n & 0xFF), (char)(n >> 8), (char)(~n & 0xFF), (char)((~n >> 8) & 0xFF)};
+        z.append(hdr, 5);
+        z.append(raw, off, n);
+        for (size_t i = 0; i < n; ++i) { a1 = (a1 + (unsigned char)raw[off + i]) % 65521u; a2 = (a2 + a1) % 65521u; }
+        if (last) break;
+      }
+      const uint32_t ad = (a2 << 16) | a1;
+      const char adl[4] = {(char)(ad >> 24), (char)(ad >> 16), (char)(ad >> 8), (char)ad};
+      z.append(adl, 4);
+      png_chunk(out, "IDAT", z);
+      png_chunk(out, "IEND", "");
+    }
+  }
+  FILE* f = path ? fopen(path, "wb") : stdout;
+  if (!f) { fail("rt_write_image: cannot open output"); return -1; }
+  const size_t w = fwrite(out.data(), 1, out.size(), f);
   if (path) fclose(f); else fflush(f);
   return (long)w;
+}
+
+extern "C" long rt_write_ppm(const char* path, const float* rgb, int32_t nx, int32_t ny, int32_t double_scale) {
+  return rt_write_image(path, rgb, nx, ny, 0, 0, double_scale);
 }

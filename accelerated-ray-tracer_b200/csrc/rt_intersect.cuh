@@ -119,8 +119,10 @@ RT_D bool box_hit(const DQuad* faces, const float4* planes, const Ray& r, float 
 // ---- instance wrappers + leaves: generic hit of a non-medium geometry ref ----
 #define RT_MAX_XFORM 4
 // known_face >= 0 (shading): the box face k_trace found; only that quad is intersected again.
-template <bool FULL, bool TIE = false>
-RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax, bool want_uv, Rec& rec, int known_face = -1) {
+// SC: anything with the geometry tables (spheres, quads, qplanes, xforms): DScene, or the GeomTab of pointers that the
+// out-of-line copy used by the traversal takes (below).
+template <bool FULL, bool TIE = false, class SC = DScene>
+RT_D bool geom_hit(const SC& S, uint32_t ref, Ray r, float tmin, float tmax, bool want_uv, Rec& rec, int known_face = -1) {
   uint32_t chain[RT_MAX_XFORM];
   V3 dir_in[RT_MAX_XFORM];  // ray direction as each rotate_y saw it (for its normal flip)
   int n = 0;
@@ -187,11 +189,12 @@ RT_D bool geom_hit(const DScene& S, uint32_t ref, Ray r, float tmin, float tmax,
 // ---- constant_medium (constant_medium.cuh:36-76), always entered through the 4-argument overload:
 // the free-flight sample comes from a throw-away XORWOW seeded by a hash of the ray (:69-74), never
 // from the pixel's stream.
-RT_D bool medium_hit(const DScene& S, const DMedium& m, const Ray& r, float tmin, float tmax, float& t_out) {
-  Rec r1, r2;
-  if (!geom_hit<false>(S, m.boundary, r, -FLT_MAX, FLT_MAX, false, r1)) return false;
-  if (!geom_hit<false>(S, m.boundary, r, fadd(r1.t, 1e-4f), FLT_MAX, false, r2)) return false;
-  float t1 = r1.t, t2 = r2.t;
+// BH: the boundary's hit routine, (tmin, tmax, float& t) -> bool.
+template <class BH>
+RT_D bool medium_hit_with(const DMedium& m, const Ray& r, float tmin, float tmax, float& t_out, BH boundary_t) {
+  float t1, t2;
+  if (!boundary_t(-FLT_MAX, FLT_MAX, t1)) return false;
+  if (!boundary_t(fadd(t1, 1e-4f), FLT_MAX, t2)) return false;
   if (t1 < tmin) t1 = tmin;
   if (t2 > tmax) t2 = tmax;
   if (t1 >= t2) return false;
@@ -207,6 +210,33 @@ RT_D bool medium_hit(const DScene& S, const DMedium& m, const Ray& r, float tmin
   if (hit_distance > distance_inside) return false;
   t_out = fadd(t1, fdiv(hit_distance, ray_len));
   return true;
+}
+
+// ONE out-of-line copy of the quad / box / instance-chain code for the traversal kernels: it is needed by the geometry
+// pass of the leaf phase and twice by every medium test, and inlined three times it pushed k_trace to 50 KB of SASS
+// against a 32 KB instruction cache. A DScene reference would have to be spilled to local memory for a real call; four
+// pointers travel in registers. Returns (bit pattern of t, face) or (0xFFFFFFFF, 0). TIE semantics (t == tmax passes):
+// the medium's boundary queries run with tmax = FLT_MAX, where that makes no difference.
+struct GeomTab { const DSphere* spheres; const DQuad* quads; const float4* qplanes; const DXform* xforms; };
+RT_D GeomTab geom_tab(const DScene& S) { GeomTab G; G.spheres = S.spheres; G.quads = S.quads; G.qplanes = S.qplanes; G.xforms = S.xforms; return G; }
+#ifndef RT_GEOM_INLINE
+__device__ __noinline__
+#else
+RT_D
+#endif
+uint2 geom_hit_call(GeomTab G, uint32_t ref, float ox, float oy, float oz, float dx, float dy, float dz, float tm, float tmin, float tmax) {
+  Ray r; r.o = v3(ox, oy, oz); r.d = v3(dx, dy, dz); r.tm = tm;
+  Rec rec; rec.face = 0;
+  if (!geom_hit<false, true>(G, ref, r, tmin, tmax, false, rec)) return make_uint2(0xFFFFFFFFu, 0u);
+  return make_uint2(f2u(rec.t), (uint32_t)rec.face);
+}
+RT_D bool medium_hit(const DScene& S, const DMedium& m, const Ray& r, float tmin, float tmax, float& t_out) {
+  const GeomTab G = geom_tab(S);
+  return medium_hit_with(m, r, tmin, tmax, t_out, [&](float a, float b, float& t) {
+    const uint2 h = geom_hit_call(G, m.boundary, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.tm, a, b);
+    t = u2f(h.x);
+    return h.x != 0xFFFFFFFFu;
+  });
 }
 
 // Is the object's own interval test inclusive at tmax (quad: t > tmax rejects) or exclusive (sphere: t < tmax)?
@@ -374,9 +404,9 @@ struct Trav {
         const bool has = kk < nl;
         if (__ballot_sync(0xFFFFFFFFu, has) == 0u) break;
         if (has && lq_tn[kk] < best.t) {
-          Rec rec; rec.face = 0;
           RT_COUNT(2, 1);
-          if (geom_hit<false, true>(S, lq_ref[kk], r, tmin, best.t, false, rec)) leaf_accept(S, lq_ref[kk], lq_tlp[kk], rec.t, rec.face, best);
+          const uint2 h = geom_hit_call(geom_tab(S), lq_ref[kk], r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.tm, tmin, best.t);
+          if (h.x != 0xFFFFFFFFu) leaf_accept(S, lq_ref[kk], lq_tlp[kk], u2f(h.x), (int)h.y, best);
         }
         ++kk;
       }

@@ -54,7 +54,7 @@ class RenderStatsC(C.Structure):
 
 EXPORTS = ["rt_build_scene", "rt_build_scene_sd", "rt_render", "rt_render_stats_get", "rt_readback", "rt_readback_t", "rt_destroy",
            "rt_last_error", "rt_scene_info_get", "rt_scene_export", "rt_scene_export_host", "rt_accum_device_ptr",
-           "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm", "rt_load_texture"]
+           "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm", "rt_load_texture", "rt_write_image", "rt_accum_reduce"]
 
 _lib = None
 
@@ -85,6 +85,9 @@ def lib():
         L.rt_fb_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.rt_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.rt_write_ppm.restype = C.c_long
+        L.rt_write_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.rt_write_image.restype = C.c_long
+        L.rt_accum_reduce.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
         L.rt_load_texture.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = L
     return _lib

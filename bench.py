@@ -55,21 +55,44 @@ def texture_dir():
     raise SystemExit("bench: earthmap.ppm not found (run __graft_entry__.build() where /root/reference exists)")
 
 
-NCU_EXTRA = {}
+MICROBENCH = os.path.join(PKG, "lib", "rt_microbench")
 
 
-def ncu_traffic_per_ray(kernel="k_trace<0>"):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the latest committed ncu capture (profiles/*_traffic.json,
-    written by tools/summarize_profile.py), per ray of that launch (grid x block threads, one ray each)."""
+def ncu_capture():
+    """Per-ray figures of k_trace / k_shade from the latest committed `ncu --set full` capture (profiles/*_traffic.json,
+    written by tools/summarize_profile.py): DRAM / L2 / L1 bytes, FP32 flop and warp instructions of one launch divided by
+    the rays of that launch, plus issue utilisation and lanes per instruction."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
-    if not files:
-        return None, None
-    d = json.load(open(files[-1])).get(kernel)
-    if not d:
-        return None, None
-    NCU_EXTRA.update({k: d.get(k) for k in ("inst_issued_pct_of_peak", "threads_per_instruction", "l1_hit_pct", "l2_hit_pct", "fma_pipe_pct")})
-    return d["dram_bytes"] / (d["grid"] * d["block"]), os.path.basename(files[-1])
+    for f in files[::-1]:
+        d = json.load(open(f))
+        kt = d.get("k_trace") or d.get("k_trace<0>")
+        ks = d.get("k_shade<0>")
+        if kt and kt.get("rays") and kt.get("warp_inst"):
+            return kt, ks, os.path.basename(f)
+    return None, None, None
+
+
+def microbench():
+    """Measured denominators (the FP32 and L2 peaks 'must be microbenchmarked'): tools/microbench.cu, run live
+    on this GPU when the binary is there (about 3 s), else the committed result of the last run on the same GPU model."""
+    if os.path.exists(MICROBENCH):
+        try:
+            r = subprocess.run([MICROBENCH], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+            for line in r.stdout.splitlines():
+                if line.startswith("{"):
+                    d = json.loads(line)
+                    d["source"] = "tools/microbench.cu run live on this GPU"
+                    return d
+        except Exception:  # noqa: BLE001
+            pass
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_microbench.json")))
+    if files:
+        d = json.load(open(files[-1]))
+        d["source"] = "profiles/" + os.path.basename(files[-1])
+        return d
+    return None
 
 
 def peaks():
@@ -236,6 +259,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-microbench", action="store_true", help="do not run tools/microbench.cu (measured FP32 / issue / L2 peaks)")
     ap.add_argument("--profile-in-timed", action="store_true",
                     help="record CUDA events around every launch INSIDE the timed region (costs ~7%%); default: the "
                          "per-kernel durations come from one extra, untimed, profiled step of the same workload")
@@ -402,13 +426,60 @@ def main():
 
     if rank == 0:
         hbm, peak_src, sm_max = peaks()
-        # dominant kernel = k_trace: algorithmic bytes per launch / mean launch duration (CUDA events on the render stream)
+        # ---- roofline of the dominant kernel, k_trace (70% of the kernel time): isolated launch duration measured live
+        # with CUDA events on the render stream (one profiled step, one pool) x per-ray figures of the committed ncu capture
         n_launch = max(waves, 1)
         rays_per_launch = prof_rays / n_launch
-        trace_s_per_launch = trace_ms / n_launch / 1e3
-        achieved = C4_TRACE_BYTES_PER_RAY * rays_per_launch / trace_s_per_launch / 1e9 if trace_ms > 0 else None
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
-        tpr, tsrc = ncu_traffic_per_ray()
+        trace_s = trace_ms / n_launch / 1e3 if trace_ms > 0 else None
+        shade_s = shade_ms / n_launch / 1e3 if shade_ms > 0 else None
+        kt, ks, ncu_src = ncu_capture()
+        mb = microbench() if not args.no_microbench else None
+        trace_rays_per_s = rays_per_launch / trace_s if trace_s else None
+        roof = {"bound": "issue", "kernel": "k_trace", "achieved": None, "peak": None, "unit": "Gwarp-inst/s", "frac": None, "traffic": None}
+        if kt and trace_rays_per_s:
+            per = lambda k, d=kt: (d[k] / d["rays"]) if d.get(k) else None  # noqa: E731
+            issue_peak = mb["issue_ginst_s"] if mb else 148 * 4 * sm_max / 1e3
+            ach = per("warp_inst") * trace_rays_per_s / 1e9
+            roof.update({
+                "achieved": round(ach, 1), "peak": round(issue_peak, 1), "frac": round(ach / issue_peak, 4),
+                "traffic": round(per("dram_bytes") * rays_per_launch),
+                "what": "k_trace is bound by instruction issue, not by a memory level or the FP32 lanes: achieved = warp "
+                        "instructions per ray (ncu capture) x rays per second of the isolated launch (CUDA events, this run); "
+                        "peak = measured issue rate of the whole GPU (1 warp instruction per scheduler per clock)",
+                "peak_source": mb["source"] if mb else "148 SMs x 4 schedulers x sm_max_mhz (data sheet)",
+                "ncu_source": "profiles/" + ncu_src,
+                "warp_inst_per_ray": round(per("warp_inst"), 1), "lanes_per_instruction": kt.get("threads_per_instruction"),
+                "useful_lane_frac": round(ach / issue_peak * kt["threads_per_instruction"] / 32.0, 4),
+                "rays_per_launch": round(rays_per_launch, 1), "launch_ms": round(trace_ms / n_launch, 5),
+                "mrays_per_s_isolated": round(trace_rays_per_s / 1e6, 1),
+                "share_of_kernel_time": {"k_trace": round(trace_ms / max(trace_ms + shade_ms, 1e-9), 4),
+                                         "k_shade": round(shade_ms / max(trace_ms + shade_ms, 1e-9), 4)},
+                # the other roofs of the same kernel, each achieved / MEASURED peak (all well below 1: none of them binds)
+                "fp32": {"achieved_tflops": round(per("flop") * trace_rays_per_s / 1e12, 2),
+                         "peak_tflops": mb["fp32_fma_tflops"] if mb else round(148 * 128 * 2 * sm_max / 1e6, 1),
+                         "flop_per_ray": round(per("flop"), 1)},
+                "l1": {"achieved_gbs": round(per("l1_bytes") * trace_rays_per_s / 1e9, 1), "peak_gbs": mb["l1_read_gbs"] if mb else None,
+                       "bytes_per_ray": round(per("l1_bytes"), 1), "hit_pct": kt.get("l1_hit_pct")},
+                "l2": {"achieved_gbs": round(per("l2_bytes") * trace_rays_per_s / 1e9, 1), "peak_gbs": mb["l2_read_gbs"] if mb else None,
+                       "bytes_per_ray": round(per("l2_bytes"), 1), "hit_pct": kt.get("l2_hit_pct")},
+                "hbm": {"achieved_gbs": round(per("dram_bytes") * trace_rays_per_s / 1e9, 1), "peak_gbs": hbm, "peak_source": peak_src,
+                        "bytes_per_ray": round(per("dram_bytes"), 1),
+                        "algorithmic_bytes_per_ray": 40, "algorithmic": "ray read 32 B + hit write 8 B (the scene is cache-resident)"},
+            })
+            for k in ("fp32", "l1", "l2", "hbm"):
+                a_, p_ = (roof[k].get("achieved_tflops") or roof[k].get("achieved_gbs")), (roof[k].get("peak_tflops") or roof[k].get("peak_gbs"))
+                roof[k]["frac"] = round(a_ / p_, 4) if a_ and p_ else None
+            if ks and shade_s:
+                sr = rays_per_launch / shade_s
+                roof["k_shade"] = {"bound": "hbm latency (gathers in queue order)", "mrays_per_s_isolated": round(sr / 1e6, 1),
+                                   "hbm_achieved_gbs": round(ks["dram_bytes"] / ks["rays"] * sr / 1e9, 1), "hbm_peak_gbs": hbm,
+                                   "hbm_frac": round(ks["dram_bytes"] / ks["rays"] * sr / 1e9 / hbm, 4),
+                                   "dram_bytes_per_ray": round(ks["dram_bytes"] / ks["rays"], 1), "algorithmic_bytes_per_ray": 140,
+                                   "algorithmic": "read 4 x float4 state + float2 hit + int queue entry = 76 B, write 4 x float4 = 64 B"}
+            # labelled extra (round-1 figure): what the REFERENCE algorithm would have to move per ray if nothing were cached
+            roof["hbm_equivalent_of_reference_algorithm"] = {
+                "bytes_per_ray": C4_TRACE_BYTES_PER_RAY, "gbs": round(C4_TRACE_BYTES_PER_RAY * trace_rays_per_s / 1e9, 1),
+                "note": "SURVEY.md 8d normaliser; NOT a roof of this kernel (the scene is L1/L2-resident), kept for comparison with round 1"}
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(span_ms / K, 3), "higher_is_better": True, "scaling": "weak" if weak else "strong",
@@ -428,24 +499,8 @@ def main():
             "clocks": ck,
             "parity_check": parity,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 1) if achieved else None,
-                         "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4) if achieved else None,
-                         "traffic": round(tpr * rays_per_launch) if tpr else None,
-                         "traffic_source": ("ncu dram bytes/ray of %s x rays per launch" % tsrc) if tpr else None,
-                         "peak_source": peak_src,
-                         "binding_resource": {"what": "instruction issue (not HBM, not FP32 lanes): ncu metrics of the same kernel from "
-                                                      "the committed capture", **NCU_EXTRA} if NCU_EXTRA else None,
-                         "algorithmic_bytes_per_ray": C4_TRACE_BYTES_PER_RAY,
-                         "rays_per_launch": round(rays_per_launch, 1), "launch_ms": round(trace_ms / n_launch, 5),
-                         "share_of_kernel_time": {"k_trace": round(trace_ms / max(trace_ms + shade_ms, 1e-9), 4),
-                                                  "k_shade": round(shade_ms / max(trace_ms + shade_ms, 1e-9), 4)},
-                         "note": "achieved = HBM-EQUIVALENT algorithmic bytes of the reference algorithm (SURVEY.md 8d); the scene is "
-                                 "L1/L2-resident, so frac can exceed 1 and the DRAM traffic is only the path state; the kernel is "
-                                 "issue-bound (profiles/README.md), see roofline_fp32 for the ALU roof"},
-            "roofline_fp32": {"achieved_tflops": round(value * 1e6 / world * C4_FLOP_PER_RAY / 1e12, 3),
-                              "peak_tflops": round(fp32_peak, 1),
-                              "frac": round(value * 1e6 / world * C4_FLOP_PER_RAY / 1e12 / fp32_peak, 4),
-                              "flop_per_ray": C4_FLOP_PER_RAY, "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz"},
+            "roofline": roof,
+            "microbench": mb,
         }
         if world == 1 and not args.no_reference_cuda:
             sc.close()

@@ -30,7 +30,8 @@ typedef struct rt_scene_desc {
   int32_t nx, ny;          /* <= 0: the scene function's own resolution; nx/ny feeds the camera aspect */
   int32_t grid_half;       /* scene 1 only: GRID_MIN/MAX (main.cu:140-141); <= 0 means 11 (488 spheres) */
   int32_t device;          /* CUDA device ordinal; < 0: current device */
-  const char* texture_dir; /* directory with <name>.ppm (P6) textures; NULL = "textures" (main.cu:1186) */
+  const char* texture_dir; /* directory with the reference's <name>.jpg textures (or pre-decoded <name>.ppm, P6);
+                              NULL = "textures" relative to the CWD like the reference (main.cu:1186) */
 } rt_scene_desc;
 
 /* Replaces the arguments of render<<<>>> and the per-scene constants (main.cu:107-109, 1179, 1208). */
@@ -46,7 +47,7 @@ typedef struct rt_render_params {
   int32_t rng_mode;        /* 0 = Philox4x32-10 (counter based), 1 = reference XORWOW streams, curand_init(1984+pixel,0,0) */
   int32_t split_mode;      /* 0 = tile split (rank owns scanlines j = rank mod world), 1 = spp split */
   int32_t rank, world;     /* this process's share; world <= 0 means 1 */
-  int32_t slots;           /* Philox mode: path slots in flight; <= 0: automatic (2 Mi). Reference-RNG mode: one per pixel */
+  int32_t slots;           /* Philox mode: path slots in flight; <= 0: automatic (8 Mi). Reference-RNG mode: one per pixel */
   int32_t aov;             /* != 0: also produce primary-hit object id / material id / t buffers */
   int32_t accumulate;      /* != 0: progressive pass: the linear sums of this call are ADDED to the accumulation buffer of the
                               previous call (same resolution and split); resolve with rt_resolve(total spp so far) */
@@ -108,6 +109,11 @@ int rt_scene_export_host(const rt_scene_desc* desc, void* buf, size_t cap, size_
  * buffer of rows_local*nx*3 floats that the caller may reduce across ranks (NCCL) before resolving. */
 int rt_accum_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
 int rt_resolve(rt_scene* s, int32_t total_spp, float gamma); /* accum -> framebuffer: /ns, gamma (main.cu:128-132) */
+/* Spp split inside ONE process (one rt_scene per device, each rendered with split_mode = 1 and its own rank): adds the
+ * accumulation buffers of src[0..n_src) into dst's on dst's device - the add kernel reads the peers' buffers directly over
+ * NVLink when peer access is available, else through one cudaMemcpyPeerAsync each. Then rt_resolve(dst, total spp).
+ * (Across processes the same sum is an NCCL reduce on rt_accum_device_ptr, see pyrt/dist.py.) */
+int rt_accum_reduce(rt_scene* dst, rt_scene* const* src, int32_t n_src);
 /* Device address of this rank's framebuffer share (rows_local*nx*3 floats), e.g. for an NCCL gather of tiles. */
 int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
 
@@ -124,6 +130,10 @@ int rt_load_texture(const char* path, unsigned char* rgb, size_t cap, int32_t* w
  * int(255.99f*c) per channel, no clamp. rgb is a FULL image (ny*nx*3, row 0 = bottom). double_scale != 0
  * reproduces bouncing_spheres' `int(255.99*c)` in double (main.cu:722-724). Returns bytes written or < 0. */
 long rt_write_ppm(const char* path /* NULL = stdout */, const float* rgb, int32_t nx, int32_t ny, int32_t double_scale);
+/* The optional outputs next to it: format 0 = that P3 text (clamp != 0 limits the integers to 0..255, which the reference
+ * does not do), 1 = binary P6, 2 = PNG (8-bit RGB, stored deflate blocks; no external library). P6 / PNG always clamp. */
+long rt_write_image(const char* path /* NULL = stdout */, const float* rgb, int32_t nx, int32_t ny, int32_t format, int32_t clamp,
+                    int32_t double_scale);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,9 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.oracle_load.restype = C.c_void_p
         L.oracle_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int]
+        L.oracle_load2.restype = C.c_void_p
+        L.oracle_load2.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int, C.c_int]
+        L.oracle_primary_ids_brute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_n_top.argtypes = [C.c_void_p]
         L.oracle_n_nodes.argtypes = [C.c_void_p]
@@ -41,11 +44,12 @@ def load_ppm(path):
 
 
 class Oracle:
-    def __init__(self, sd_bytes, images=()):
+    def __init__(self, sd_bytes, images=(), bvh=True):
+        """bvh=False: skip the reference's O(n^2)-per-level BVH constructor (large scenes); only primary_ids_brute works."""
         self._sd = bytes(sd_bytes)
         self._imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
         arr = (C.c_void_p * max(len(self._imgs), 1))(*[im.ctypes.data for im in self._imgs])
-        self._h = lib().oracle_load(self._sd, len(self._sd), arr, len(self._imgs))
+        self._h = lib().oracle_load2(self._sd, len(self._sd), arr, len(self._imgs), 1 if bvh else 0)
         if not self._h:
             raise ValueError("oracle_load: bad scene description")
         self.n_top = lib().oracle_n_top(self._h)
@@ -72,6 +76,14 @@ class Oracle:
         mat = np.empty((ny, nx), dtype=np.int32)
         t = np.empty((ny, nx), dtype=np.float32)
         lib().oracle_primary_ids(self._h, nx, ny, obj.ctypes.data, mat.ctypes.data, t.ctypes.data)
+        return obj, mat, t
+
+    def primary_ids_brute(self, nx, ny):
+        """Same query as primary_ids with no hierarchy at all: every object, in creation order, behind its own box test."""
+        obj = np.empty((ny, nx), dtype=np.int32)
+        mat = np.empty((ny, nx), dtype=np.int32)
+        t = np.empty((ny, nx), dtype=np.float32)
+        lib().oracle_primary_ids_brute(self._h, nx, ny, obj.ctypes.data, mat.ctypes.data, t.ctypes.data)
         return obj, mat, t
 
     def render(self, nx, ny, spp, background=(0, 0, 0), gradient=False, max_depth=50, gamma=2.2):

@@ -516,7 +516,13 @@ inline float apply_gamma(float c, float gamma) {  // main.cu:37-42
 extern "C" {
 
 // images: n_img pointers to decoded 8-bit pixels (may be NULL when no texture is an image)
+void* oracle_load2(const void* sd, size_t len, const unsigned char* const* images, int n_images, int with_bvh);
 void* oracle_load(const void* sd, size_t len, const unsigned char* const* images, int n_images) {
+  return oracle_load2(sd, len, images, n_images, 1);
+}
+// with_bvh = 0: no reference BVH (its constructor is O(n^2) per level, bvh.cuh:66-77 - hours at 10^6 objects); only
+// oracle_primary_ids_brute may be called on such a scene.
+void* oracle_load2(const void* sd, size_t len, const unsigned char* const* images, int n_images, int with_bvh) {
   if (!sd || len < sizeof(rt_sd_header)) return nullptr;
   Scene* S = new Scene();
   const unsigned char* p = (const unsigned char*)sd;
@@ -535,7 +541,7 @@ void* oracle_load(const void* sd, size_t len, const unsigned char* const* images
   const int n = (int)S->top.size();
   S->order.resize(n);
   for (int i = 0; i < n; ++i) S->order[i] = i;
-  if (n > 0) { S->nodes.reserve(2 * n); build_bvh(*S, S->order, 0, n); }
+  if (n > 0 && with_bvh) { S->nodes.reserve(2 * n); build_bvh(*S, S->order, 0, n); }
   return S;
 }
 void oracle_free(void* h) { delete (Scene*)h; }
@@ -567,6 +573,44 @@ void oracle_primary_ids(void* h, int nx, int ny, int* obj, int* mat, float* t) {
       obj[pix] = hit ? rec.top : -1;
       mat[pix] = hit ? rec.mat : -1;
       t[pix] = hit ? rec.t : 0.f;
+    }
+}
+
+// The same query WITHOUT any hierarchy: every top-level object in creation order, each behind its own box test
+// (aabb::hit on the object's bounding box = the leaf node's box, bvh.cuh:38-43) and hit twice like a leaf node
+// (left == right, bvh.cuh:100-105), t_max shrinking as hits are found. Equals oracle_primary_ids except for exact-t ties
+// between different objects (decided by visiting order). For the C5 scale-up scenes, whose reference BVH cannot be built.
+void oracle_primary_ids_brute(void* h, int nx, int ny, int* obj, int* mat, float* t) {
+  const Scene& S = *(Scene*)h;
+  const rt_camera_desc& c = S.h.cam;
+  const int n = (int)S.top.size();
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i) {
+      const float s = ((float)i + 0.5f) / (float)nx, tt = ((float)j + 0.5f) / (float)ny;
+      ray r;
+      r.A = V3(c.origin);
+      r.B = madd(tt, V3(c.vertical), madd(s, V3(c.horizontal), V3(c.lower_left_corner))) - V3(c.origin);
+      r.tm = (float)c.time0;
+      float closest = FLT_MAX;
+      hit_record best;
+      int best_top = -1;
+      for (int k = 0; k < n; ++k) {
+        const int o = S.top[k];
+        if (!aabb_hit(obj_box(S, o), r, 0.001f, closest)) continue;
+        hit_record lrec, rrec;
+        const bool hl = object_hit(S, o, r, 0.001f, closest, lrec);
+        const bool hr = object_hit(S, o, r, 0.001f, hl ? lrec.t : closest, rrec);
+        if (!hl && !hr) continue;
+        hit_record rec;
+        if (hr) rec = rrec;
+        if (hl && (!hr || lrec.t < rrec.t)) rec = lrec;
+        best = rec; best_top = k; closest = rec.t;
+      }
+      const int pix = j * nx + i;
+      obj[pix] = best_top;
+      mat[pix] = best_top >= 0 ? best.mat : -1;
+      t[pix] = best_top >= 0 ? best.t : 0.f;
     }
 }
 

@@ -75,8 +75,19 @@ def test_reference_rng_mode_matches_reference_cuda_build(pyrt, golden, name, sid
         assert nbad <= 0.005 * nx * ny and float(np.abs(fb - gfb).max()) <= 2.4e-7
     else:
         assert nbad == 0, "%d pixels differ in the float framebuffer" % nbad
-    # 4. same ray count as the reference's bounce loop (golden log)
-    assert st.rays > 0 and st.stack_overflow == 0
+    # 4. same ray count as the reference's bounce loop (the golden run's log: tests/golden/ref_gpu/results.jsonl)
+    assert st.stack_overflow == 0
+    want_rays = _golden_rays(sid, nx, ny, spp)
+    assert want_rays is not None and st.rays == want_rays, (st.rays, want_rays)
+
+
+def _golden_rays(sid, nx, ny, spp):
+    import json
+    for l in open(os.path.join(os.path.dirname(__file__), "golden", "ref_gpu", "results.jsonl")):
+        d = json.loads(l)
+        if (d.get("scene"), d.get("nx"), d.get("ny"), d.get("ns")) == (sid, nx, ny, spp) and d.get("rays", 0) > 0:
+            return int(d["rays"])
+    return None
 
 
 FULL_ID_CASES = [("c2_600x600_ids", 7, 600, 600), ("c3_600x600_ids", 8, 600, 600), ("c4_800x800_ids", 9, 800, 800)]
@@ -245,6 +256,38 @@ def test_scale_up_c5_bvh_matches_brute_force_ids(pyrt, built):
     o_obj, o_mat, o_t = oracle_py.primary_ids(sd.raw.tobytes(), 320, 180)
     assert np.array_equal(o_obj, obj)
     assert np.array_equal(o_t.view(np.uint32), t.view(np.uint32))
+
+
+@pytest.mark.parametrize("grid_half,n_top,nx,ny", [(158, 99860, 96, 54), (500, 1000004, 64, 36)], ids=["100k", "1M"])
+def test_scale_up_c5_large_matches_brute_force(pyrt, built, monkeypatch, grid_half, n_top, nx, ny):
+    """C5 at 10^5 and 10^6 spheres (main.cu:160-244 with GRID_MIN/MAX widened, :140-141): the reference cannot build these
+    scenes (its BVH constructor is a per-level selection sort in one device thread), so the oracle answers the primary-hit
+    query with NO hierarchy - every sphere, each behind its own box test. Object id, material and the bit pattern of t must
+    match for every pixel, for the PLOC build and for the radix-tree build (two different topologies over the same
+    leaves), the traversal stack must not overflow, and full path tracing on the two builds must produce the same image."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle"))
+    import oracle_py
+    res = {}
+    for builder in ("ploc", "lbvh"):
+        monkeypatch.setenv("RT_BVH_BUILDER", builder)
+        with _scene(pyrt, 1, nx, ny, grid_half=grid_half) as sc:
+            assert sc.info.n_top == n_top
+            sd, rank = sc.export()
+            st = sc.render(spp=8, rng_mode=0, aov=True)
+            assert st.stack_overflow == 0 and st.nonfinite_samples == 0
+            res[builder] = (sc.aov(), sc.framebuffer(), st.rays, sc.info.n_bvh_nodes)
+    o = oracle_py.Oracle(sd.raw.tobytes(), bvh=False)
+    o_obj, o_mat, o_t = o.primary_ids_brute(nx, ny)
+    assert (o_obj >= 0).mean() > 0.5
+    for builder, ((obj, mat, t), fb, rays, nodes) in res.items():
+        assert np.array_equal(o_obj, obj), builder
+        assert np.array_equal(o_mat, mat), builder
+        assert np.array_equal(o_t.view(np.uint32), t.view(np.uint32)), builder
+    # same leaves, same closest hits => the same paths to the last ray, whatever the tree looks like
+    assert res["ploc"][3] != res["lbvh"][3] or grid_half == 0
+    assert res["ploc"][2] == res["lbvh"][2]
+    assert np.array_equal(res["ploc"][1].view(np.uint32), res["lbvh"][1].view(np.uint32))
 
 
 def test_scene_reads_the_references_jpg_textures(pyrt):

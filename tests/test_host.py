@@ -94,6 +94,52 @@ def test_jpeg_decoder_rejects_what_it_cannot_decode_exactly(pyrt, tmp_path):
             pyrt.load_texture(str(tmp_path / "hdr.jpg"))
 
 
+def test_image_writers_p3_p6_png(pyrt, tmp_path):
+    """rt_write_image: P3 is the reference's text (unclamped unless asked), P6 and PNG carry the same clamped bytes;
+    the PNG is decoded back here with zlib and checked chunk by chunk (CRC, Adler, IHDR)."""
+    import struct, zlib
+    rng = np.random.default_rng(3)
+    nx, ny = 37, 23
+    img = rng.random((ny, nx, 3), dtype=np.float32) * 1.3 - 0.1   # values below 0 and above 1
+    L = pyrt.lib()
+    want = np.clip((np.float32(255.99) * img).astype(np.int64), 0, 255).astype(np.uint8)[::-1]   # top row first
+    unclamped = (np.float32(255.99) * img).astype(np.int64)[::-1]
+    paths = {k: str(tmp_path / ("o." + k)).encode() for k in ("p3", "p3c", "p6", "png")}
+    assert L.rt_write_image(paths["p3"], img.ctypes.data, nx, ny, 0, 0, 0) > 0
+    assert L.rt_write_image(paths["p3c"], img.ctypes.data, nx, ny, 0, 1, 0) > 0
+    assert L.rt_write_image(paths["p6"], img.ctypes.data, nx, ny, 1, 0, 0) > 0
+    assert L.rt_write_image(paths["png"], img.ctypes.data, nx, ny, 2, 0, 0) > 0
+    tok = open(paths["p3"]).read().split()
+    assert tok[:4] == ["P3", str(nx), str(ny), "255"]
+    assert np.array_equal(np.array(tok[4:], dtype=np.int64).reshape(ny, nx, 3), unclamped)
+    assert unclamped.max() > 255 and unclamped.min() <= 0
+    tokc = open(paths["p3c"]).read().split()
+    assert np.array_equal(np.array(tokc[4:], dtype=np.int64).reshape(ny, nx, 3), want)
+    raw = open(paths["p6"], "rb").read()
+    hdr = b"P6\n%d %d\n255\n" % (nx, ny)
+    assert raw.startswith(hdr) and np.array_equal(np.frombuffer(raw[len(hdr):], dtype=np.uint8).reshape(ny, nx, 3), want)
+    png = open(paths["png"], "rb").read()
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    off, chunks = 8, []
+    while off < len(png):
+        n, typ = struct.unpack(">I4s", png[off:off + 8])
+        data = png[off + 8:off + 8 + n]
+        assert struct.unpack(">I", png[off + 8 + n:off + 12 + n])[0] == zlib.crc32(typ + data)
+        chunks.append((typ, data))
+        off += 12 + n
+    assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+    assert struct.unpack(">IIBBBBB", chunks[0][1]) == (nx, ny, 8, 2, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(chunks[1][1]), dtype=np.uint8).reshape(ny, 1 + 3 * nx)
+    assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(ny, nx, 3), want)
+    big = np.zeros((300, 300, 3), dtype=np.float32)   # > 65535 bytes: several stored deflate blocks
+    assert L.rt_write_image(paths["png"], big.ctypes.data, 300, 300, 2, 0, 0) > 0
+    png = open(paths["png"], "rb").read()
+    i = png.index(b"IDAT")
+    n = struct.unpack(">I", png[i - 4:i])[0]
+    assert len(zlib.decompress(png[i + 4:i + 4 + n])) == 300 * 901
+    assert L.rt_write_image(paths["png"], img.ctypes.data, nx, ny, 7, 0, 0) < 0  # unknown format
+
+
 def test_no_cpu_fallback(pyrt):
     """Without a CUDA device the render path must fail loudly, not fall back."""
     import torch

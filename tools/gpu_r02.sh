@@ -33,3 +33,6 @@ if [[ $WHAT == *ncu* ]]; then
   echo "ncu full rc=$?"; tail -2 $O/ncu_full.log
 fi
 ls -la $O | tail -8
+if [[ $WHAT == *configs* ]]; then
+  timeout 900 python tools/all_configs.py 2>&1 | tee $O/all_configs_$TAG.jsonl
+fi

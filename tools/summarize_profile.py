@@ -75,7 +75,19 @@ if os.path.exists(rep):
                       "inst_issued_pct_of_peak": num(r[hdr.index("sm__inst_issued.avg.pct_of_peak_sustained_active")]) if "sm__inst_issued.avg.pct_of_peak_sustained_active" in hdr else None,
                       "threads_per_instruction": num(r[hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")]),
                       "l1_hit_pct": num(r[hdr.index("l1tex__t_sector_hit_rate.pct")]), "l2_hit_pct": num(r[hdr.index("lts__t_sector_hit_rate.pct")]),
-                      "fma_pipe_pct": num(r[hdr.index("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")])}
+                      "fma_pipe_pct": num(r[hdr.index("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")]),
+                      "warp_inst": num(r[hdr.index("smsp__inst_executed.sum")]),
+                      "l2_bytes": 32.0 * num(r[hdr.index("lts__t_sectors.sum")]) if "lts__t_sectors.sum" in hdr else None,
+                      "l1_bytes": 32.0 * num(r[hdr.index("SM_B.TriageCompute.l1tex__t_sectors.sum")]) if "SM_B.TriageCompute.l1tex__t_sectors.sum" in hdr else None,
+                      # FP32 flop of the launch: (2 x FFMA + FADD + FMUL thread instructions per cycle) x elapsed cycles
+                      "flop": (sum((2.0 if "ffma" in k else 1.0) * num(r[hdr.index(k)]) for k in
+                                   ("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed",
+                                    "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed",
+                                    "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed") if k in hdr) *
+                               num(r[hdr.index("smsp__cycles_elapsed.avg")])) if "smsp__cycles_elapsed.avg" in hdr else None}
+        # rays of the launch: a k_trace warp owns RT_RANGE (env, default 64) rays of the dense layout, a k_shade thread one
+        per_thread = (int(os.environ.get("RT_RANGE", "64")) / 32.0) if n.startswith("k_trace") else 1.0
+        traffic[n]["rays"] = traffic[n]["grid"] * traffic[n]["block"] * per_thread
     json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
     # ---- per-source-line attribution ----
     sass = os.path.join(G, "elf", "all_%s.sass" % tag)
