@@ -200,13 +200,21 @@ struct rt_scene {
   int n_nodes = 0; float bvh_ms = 0.f; uint64_t h2d_bytes = 0;
   // render state
   cudaStream_t stream = nullptr, pool_stream[RT_MAX_POOLS] = {nullptr};  // pool 0 runs on `stream`
-  DBuf<float4> ray_o[2], ray_d[2], thr[2], rad[2], col; DBuf<float2> hit; DBuf<uint32_t> rng;
+  DBuf<float4> ray_o[2], ray_d[2], thr[2], col; DBuf<float2> hit; DBuf<uint32_t> rng;
   DBuf<int> queues;
   DBuf<WaveCounters> counters;          // one per slot pool
   DBuf<unsigned long long> next_work;
   WaveCounters* h_counters = nullptr;  // pinned, one per slot pool
   DBuf<float> accum, fb, aov_t, reduce_tmp; DBuf<int> aov_obj, aov_mat; DBuf<unsigned long long> acc64;
   size_t slots_cap = 0, pix_cap = 0, accum_valid_pix = 0;
+  // adaptive sampling (rt_render_adaptive): state of the pass rt_render is asked to run
+  struct Adaptive {
+    bool on = false, first = false;   // first: zero the fixed-point sums
+    int sample_base = 0, sample_count = 0, n_active = 0;
+    DBuf<int> active; DBuf<unsigned long long> acc64_odd;
+    std::vector<int> tile_spp;        // per tile of the last adaptive render (rt_readback_spp)
+    int tile = 0, tiles_x = 0, tiles_y = 0;
+  } adapt;
   RenderParams last{}; rt_render_stats stats{}; bool has_aov = false; float last_gamma = 2.2f; int last_spp_total = 0;
   ~rt_scene() {
     // kernels of a failed rt_render may still be in flight on the pool streams: nothing goes back to the block cache
@@ -259,6 +267,8 @@ struct Flattener {
         xforms.push_back(x);
         return make_ref(G_XFORM, (uint32_t)xforms.size() - 1);
       }
+      case RT_OBJ_WITH_MATERIAL:  // geometry of the child; the override lives in the top-level entry (upload_scene)
+        return flatten(o.child);
       case RT_OBJ_MEDIUM: {
         DMedium m; m.boundary = flatten(o.child); m.neg_inv_density = o.neg_inv_density; m.mat = o.mat; m.pad = 0;
         media.push_back(m);
@@ -307,7 +317,9 @@ static int upload_scene(rt_scene* s) {
   for (int k = 0; k < n; ++k) {
     const rt_object_desc& o = sd.obj[sd.top[k]];
     tlp[k].ref = F.flatten(sd.top[k]);
-    int mid = sd.top[k];  // instance wrappers carry no material of their own: take the wrapped object's
+    // instance wrappers carry no material of their own: the wrapped object's, unless a with_material sits on the way down
+    // (hittable.cuh:170-174 sets rec.mat_ptr after the child's hit, so the outermost override wins)
+    int mid = sd.top[k];
     while (sd.obj[mid].kind == RT_OBJ_TRANSLATE || sd.obj[mid].kind == RT_OBJ_ROTATE_Y) mid = sd.obj[mid].child;
     const int mat = sd.obj[mid].mat;
     if (mat < 0 || mat >= (int)sd.mat.size()) return fail("upload_scene: top-level object without a material");
@@ -552,7 +564,7 @@ static int ensure_buffers(rt_scene* s, size_t n_slots, size_t n_pix, bool ref_rn
     s->rng.free();
     // worst case over the pool counts: RT_MAX_POOLS pools, each with its own padding
     const size_t cap = pool_cap(n_slots) + RT_MAX_POOLS * pool_cap(0);
-    for (int k = 0; k < 2; ++k) { CU(s->ray_o[k].alloc(cap)); CU(s->ray_d[k].alloc(cap)); CU(s->thr[k].alloc(cap)); CU(s->rad[k].alloc(cap)); }
+    for (int k = 0; k < 2; ++k) { CU(s->ray_o[k].alloc(cap)); CU(s->ray_d[k].alloc(cap)); CU(s->thr[k].alloc(cap)); }
     CU(s->hit.alloc(cap));
     CU(s->queues.alloc((size_t)RT_NQ * (pool_subcap(n_slots) + RT_MAX_POOLS * pool_subcap(0))));
     s->slots_cap = n_slots;
@@ -590,7 +602,13 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     P.sample_base = 0; P.sample_count = spp_total;
   }
   const size_t n_pix = (size_t)P.rows_local * P.nx;
-  P.work_total = (long long)n_pix * P.sample_count;
+  const bool adaptive = s->adapt.on;
+  if (adaptive) {  // one pass of rt_render_adaptive: its own sample numbers, over the pixels of the tiles still active
+    if (ref_rng) return fail("rt_render: adaptive passes need the counter-based RNG (rng_mode 0)");
+    P.sample_base = s->adapt.sample_base; P.sample_count = s->adapt.sample_count;
+    P.active = s->adapt.active.p; P.n_active = s->adapt.n_active;
+  }
+  P.work_total = (long long)(adaptive ? (size_t)P.n_active : n_pix) * P.sample_count;
   if (ref_rng) {
     P.n_slots = (int)n_pix;  // a slot is a pixel: one sequential XORWOW stream each
   } else {
@@ -600,6 +618,8 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     P.n_slots = (int)std::max<long long>(0, std::min<long long>(target, P.work_total));
   }
   P.max_depth = p->max_depth > 0 ? p->max_depth : 50;
+  if (P.max_depth > 255) return fail("rt_render: max_depth above 255 (the bounce count shares a state word with the sample number)");
+  if ((long long)P.sample_base + P.sample_count >= (1 << 23)) return fail("rt_render: sample numbers above 2^23 (split the job into progressive passes)");
   P.tmin = p->t_min > 0 ? p->t_min : 0.001f;
   if (p->override_background) { P.background = v3(p->background[0], p->background[1], p->background[2]); P.gradient = p->gradient_bg; }
   else { P.background = v3(sd.background[0], sd.background[1], sd.background[2]); P.gradient = sd.gradient_bg; }
@@ -617,6 +637,10 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   PathArrays A;
   memset(&A, 0, sizeof(A));
   A.col = s->col.p; A.rng = s->rng.p; A.acc64 = s->acc64.p; A.next_work = s->next_work.p;
+  if (adaptive) {
+    if (s->adapt.acc64_odd.n < 3 * n_pix) CU(s->adapt.acc64_odd.alloc(3 * n_pix));
+    A.acc64_odd = s->adapt.acc64_odd.p;
+  }
   cudaStream_t st = s->stream;
   cudaStream_t* streams = s->pool_stream;
   cudaEvent_t e0, e1, evs[RT_MAX_POOLS];
@@ -635,7 +659,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
       const int n = (k == n_pools - 1) ? P.n_slots - base : std::min(per, P.n_slots - base);
       Pp[k] = P; Pp[k].n_slots = n;
       Ap[k] = A;
-      for (int b = 0; b < 2; ++b) { Ap[k].ray_o[b] = s->ray_o[b].p + abase; Ap[k].ray_d[b] = s->ray_d[b].p + abase; Ap[k].thr[b] = s->thr[b].p + abase; Ap[k].rad[b] = s->rad[b].p + abase; }
+      for (int b = 0; b < 2; ++b) { Ap[k].ray_o[b] = s->ray_o[b].p + abase; Ap[k].ray_d[b] = s->ray_d[b].p + abase; Ap[k].thr[b] = s->thr[b].p + abase; }
       Ap[k].hit = s->hit.p + abase;
       Ap[k].queues = s->queues.p + qbase;
       Ap[k].subcap = (int)pool_subcap(n);
@@ -650,7 +674,10 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     // the first n_slots work items are drawn by k_init; reference-RNG mode does not use the counter
     const unsigned long long first_work = (unsigned long long)P.n_slots;
     CU(cudaMemcpyAsync(s->next_work.p, &first_work, sizeof(first_work), cudaMemcpyHostToDevice, st));
-    if (!ref_rng && n_pix > 0) CU(cudaMemsetAsync(s->acc64.p, 0, 3 * n_pix * sizeof(unsigned long long), st));
+    if (!ref_rng && n_pix > 0 && (!adaptive || s->adapt.first)) {
+      CU(cudaMemsetAsync(s->acc64.p, 0, 3 * n_pix * sizeof(unsigned long long), st));
+      if (adaptive) CU(cudaMemsetAsync(s->adapt.acc64_odd.p, 0, 3 * n_pix * sizeof(unsigned long long), st));
+    }
   }
   const int B = RT_BLOCK;
   int launches = 0, waves = 0, prof_waves = 0;
@@ -759,7 +786,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   s->last = P; s->has_aov = p->aov != 0; s->last_gamma = gamma; s->last_spp_total = spp_total;
   rt_render_stats& R = s->stats;
   memset(&R, 0, sizeof(R));
-  R.device_ms = ms; R.rays = rays_all; R.samples = (uint64_t)n_pix * (uint64_t)P.sample_count;
+  R.device_ms = ms; R.rays = rays_all; R.samples = (uint64_t)(adaptive ? (size_t)P.n_active : n_pix) * (uint64_t)P.sample_count;
   R.waves = waves; R.kernel_launches = launches; R.rows_local = P.rows_local; R.nx = P.nx;
   R.nonfinite_samples = (int32_t)nonfinite_all; R.n_slots = P.n_slots; R.stack_overflow = overflow_all;
   R.profiled_waves = prof_waves; R.trace_ms = prof_trace_ms; R.shade_ms = prof_shade_ms;
@@ -818,6 +845,103 @@ extern "C" int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats) {
   if (n_floats) *n_floats = (size_t)s->last.rows_local * s->last.nx * 3;
   return 0;
 }
+// ---- adaptive per-tile sampling ----
+// Passes of pass_spp samples; after every pass the error of every still-active tile is estimated from the two half-buffers
+// (k_tile_error) and tiles below the threshold stop taking samples. Sample numbers are global (pass k of a tile draws
+// numbers [k * pass_spp, (k + 1) * pass_spp)), the sums are fixed-point: a tile that runs all passes holds bit for bit the
+// sums of a plain max_spp render, and with threshold = 0 the whole image equals rt_render(spp = max_spp).
+extern "C" int rt_render_adaptive(rt_scene* s, const rt_render_params* p, const rt_adaptive_params* a, rt_adaptive_stats* out) {
+  if (!s || !p || !a) return fail("rt_render_adaptive: null argument");
+  if (p->rng_mode != 0) return fail("rt_render_adaptive: needs the counter-based RNG (rng_mode 0)");
+  if (p->split_mode == 1 && p->world > 1) return fail("rt_render_adaptive: tile split only (every rank adapts its own scanlines)");
+  const int tile = a->tile > 0 ? a->tile : 16;
+  const int max_spp = a->max_spp > 0 ? a->max_spp : (p->spp > 0 ? p->spp : s->sd.default_spp);
+  const int pass_spp = std::max(2, a->pass_spp > 0 ? a->pass_spp : 16) & ~1;  // even: both half-buffers grow in every pass
+  const int min_spp = std::max(pass_spp, a->min_spp);
+  if (max_spp < pass_spp) return fail("rt_render_adaptive: max_spp below one pass");
+  CU(cudaSetDevice(s->device));
+  const int world = p->world > 0 ? p->world : 1;
+  if (p->rank < 0 || p->rank >= world) return fail("rt_render_adaptive: rank out of range");
+  const int nx = s->sd.nx, rows = (s->sd.ny - p->rank + world - 1) / world;
+  const size_t n_pix = (size_t)nx * rows;
+  const int tiles_x = (nx + tile - 1) / tile, tiles_y = (rows + tile - 1) / tile, n_tiles = tiles_x * tiles_y;
+  rt_scene::Adaptive& ad = s->adapt;
+  ad.tile = tile; ad.tiles_x = tiles_x; ad.tiles_y = tiles_y;
+  ad.tile_spp.assign(n_tiles, 0);
+  std::vector<int> n_even(n_tiles, 0), n_odd(n_tiles, 0), list;
+  std::vector<char> active(n_tiles, 1);
+  std::vector<float> err(n_tiles, 0.f);
+  DBuf<int> d_even, d_odd; DBuf<float> d_err;
+  CU(d_even.alloc(std::max(n_tiles, 1))); CU(d_odd.alloc(std::max(n_tiles, 1))); CU(d_err.alloc(std::max(n_tiles, 1)));
+  rt_render_params pp = *p;
+  pp.accumulate = 0; pp.aov = 0;
+  rt_adaptive_stats R; memset(&R, 0, sizeof(R));
+  R.tiles = n_tiles;
+  struct Off { rt_scene::Adaptive& a; ~Off() { a.on = false; } } off{ad};
+  int done = 0, rc = 0;
+  while (n_pix > 0 && done < max_spp) {
+    const int count = std::min(pass_spp, max_spp - done);
+    list.clear();
+    for (int t = 0; t < n_tiles; ++t) {
+      if (!active[t]) continue;
+      const int tx = t % tiles_x, ty = t / tiles_x;
+      for (int j = ty * tile; j < std::min(rows, (ty + 1) * tile); ++j)
+        for (int i = tx * tile; i < std::min(nx, (tx + 1) * tile); ++i) list.push_back(j * nx + i);
+    }
+    if (list.empty()) break;
+    if (ad.active.n < n_pix) CU(ad.active.alloc(n_pix));
+    CU(cudaMemcpy(ad.active.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ad.on = true; ad.first = done == 0; ad.sample_base = done; ad.sample_count = count; ad.n_active = (int)list.size();
+    if ((rc = rt_render(s, &pp, nullptr, nullptr)) != 0) return rc;
+    R.samples += s->stats.samples; R.rays += s->stats.rays; R.device_ms += s->stats.device_ms; ++R.passes;
+    // sample numbers [done, done + count): how many are odd
+    const int odd = (done + count) / 2 - done / 2, even = count - odd;
+    for (int t = 0; t < n_tiles; ++t) if (active[t]) { n_even[t] += even; n_odd[t] += odd; ad.tile_spp[t] += count; }
+    done += count;
+    if (done >= max_spp) break;
+    CU(cudaMemcpy(d_even.p, n_even.data(), n_tiles * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_odd.p, n_odd.data(), n_tiles * sizeof(int), cudaMemcpyHostToDevice));
+    k_tile_error<<<n_tiles, 256, 0, s->stream>>>(nx, rows, tile, tiles_x, s->acc64.p, ad.acc64_odd.p, d_even.p, d_odd.p, d_err.p);
+    CU(cudaMemcpyAsync(err.data(), d_err.p, n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    R.err_min = FLT_MAX; R.err_max = 0.f; R.err_spp = done;
+    for (int t = 0; t < n_tiles; ++t) if (active[t]) { R.err_min = std::min(R.err_min, err[t]); R.err_max = std::max(R.err_max, err[t]); }
+    if (done >= min_spp)
+      for (int t = 0; t < n_tiles; ++t) if (active[t] && err[t] < a->threshold) active[t] = 0;
+  }
+  ad.on = false;
+  // accum = per-pixel MEAN (every tile divides by its own sample count), framebuffer = gamma(mean)
+  if (n_pix > 0) {
+    CU(cudaMemcpy(d_even.p, n_even.data(), n_tiles * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_odd.p, n_odd.data(), n_tiles * sizeof(int), cudaMemcpyHostToDevice));
+    const int Gp = (int)((n_pix + 255) / 256);
+    PathArrays A; memset(&A, 0, sizeof(A)); A.acc64 = s->acc64.p;
+    k_accumulate<RNG_PHILOX><<<Gp, 256, 0, s->stream>>>(s->last, A, s->accum.p, 0);
+    k_normalize_tiles<<<Gp, 256, 0, s->stream>>>(nx, rows, tile, tiles_x, d_even.p, d_odd.p, s->accum.p);
+    k_resolve<<<Gp, 256, 0, s->stream>>>((int)n_pix, 1, p->gamma > 0 ? p->gamma : 2.2f, s->accum.p, s->fb.p);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    s->last_spp_total = 1;
+  }
+  int lo = 1 << 30, hi = 0; double tot = 0.0;
+  for (int t = 0; t < n_tiles; ++t) { lo = std::min(lo, ad.tile_spp[t]); hi = std::max(hi, ad.tile_spp[t]); R.tiles_converged += active[t] ? 0 : 1; }
+  tot = n_pix ? (double)R.samples / (double)n_pix : 0.0;
+  R.min_spp_used = n_tiles ? lo : 0; R.max_spp_used = hi; R.mean_spp = (float)tot;
+  s->stats.samples = R.samples; s->stats.rays = R.rays; s->stats.device_ms = R.device_ms;
+  if (out) *out = R;
+  return 0;
+}
+extern "C" int rt_readback_spp(rt_scene* s, int32_t* spp) {
+  if (!s || !spp) return fail("rt_readback_spp: null argument");
+  const rt_scene::Adaptive& ad = s->adapt;
+  if (ad.tile <= 0) return fail("rt_readback_spp: no adaptive render on this scene yet");
+  const int nx = s->last.nx, rows = s->last.rows_local;
+  for (int j = 0; j < rows; ++j)
+    for (int i = 0; i < nx; ++i) spp[(size_t)j * nx + i] = ad.tile_spp[(j / ad.tile) * ad.tiles_x + i / ad.tile];
+  return 0;
+}
+
 // ---- native multi-GPU exchange of the spp split (one process, one rt_scene per device) ----
 __global__ void k_accum_add(float* dst, const float* src, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -857,6 +981,56 @@ extern "C" int rt_accum_reduce(rt_scene* dst, rt_scene* const* src, int32_t n_sr
   }
   CU(cudaStreamSynchronize(dst->stream));
   CU(cudaGetLastError());
+  return 0;
+}
+
+// ---- dynamic tile queue over the devices of one process ----
+// The image is cut into n_chunks shares of interleaved scanlines (share c = rows j = c mod n_chunks, the tile split of
+// rt_render_params with world = n_chunks). One host thread per scene replica pulls the next share from a shared counter,
+// renders it and copies its rows into the caller's full image, until none is left: a GPU that is slower, busier, or
+// got the expensive rows simply takes fewer shares. Which device rendered which share does not change a single bit
+// (a share's samples depend on pixel and sample number only).
+#include <atomic>
+#include <thread>
+extern "C" int rt_render_queue(rt_scene* const* scenes, int32_t n_scenes, const rt_render_params* p, int32_t n_chunks, float* rgb_full,
+                               rt_queue_stats* out) {
+  if (!scenes || n_scenes <= 0 || !p || !rgb_full) return fail("rt_render_queue: null argument");
+  if (n_scenes > RT_QUEUE_MAX_DEVICES) return fail("rt_render_queue: too many scene replicas");
+  if (p->split_mode != 0) return fail("rt_render_queue: the queue hands out tile shares (split_mode 0)");
+  for (int k = 0; k < n_scenes; ++k) {
+    if (!scenes[k]) return fail("rt_render_queue: null scene");
+    if (scenes[k]->sd.nx != scenes[0]->sd.nx || scenes[k]->sd.ny != scenes[0]->sd.ny) return fail("rt_render_queue: the replicas differ in resolution");
+  }
+  const int nx = scenes[0]->sd.nx, ny = scenes[0]->sd.ny;
+  if (n_chunks <= 0) n_chunks = std::min(ny, 8 * n_scenes);
+  n_chunks = std::min(n_chunks, ny);
+  std::atomic<int> next(0);
+  rt_queue_stats R; memset(&R, 0, sizeof(R));
+  R.n_chunks = n_chunks;
+  std::vector<std::string> errs(n_scenes);
+  std::vector<std::thread> th;
+  for (int k = 0; k < n_scenes; ++k)
+    th.emplace_back([&, k]() {
+      rt_scene* s = scenes[k];
+      std::vector<float> share;
+      for (;;) {
+        const int c = next.fetch_add(1);
+        if (c >= n_chunks) break;
+        rt_render_params pp = *p;
+        pp.rank = c; pp.world = n_chunks; pp.split_mode = 0; pp.accumulate = 0;
+        if (rt_render(s, &pp, nullptr, nullptr) != 0) { errs[k] = rt_last_error(); next.store(n_chunks); break; }
+        const int rows = s->stats.rows_local;
+        share.resize((size_t)rows * nx * 3);
+        if (rt_readback(s, share.data(), nullptr, nullptr) != 0) { errs[k] = rt_last_error(); next.store(n_chunks); break; }
+        for (int lr = 0; lr < rows; ++lr)
+          memcpy(rgb_full + (size_t)(lr * n_chunks + c) * nx * 3, share.data() + (size_t)lr * nx * 3, (size_t)nx * 3 * sizeof(float));
+        R.chunks_per_device[k] += 1; R.device_ms[k] += s->stats.device_ms; R.rays_per_device[k] += s->stats.rays;
+      }
+    });
+  for (auto& t : th) t.join();
+  for (int k = 0; k < n_scenes; ++k) if (!errs[k].empty()) return fail("rt_render_queue: replica " + std::to_string(k) + ": " + errs[k]);
+  for (int k = 0; k < n_scenes; ++k) R.rays += R.rays_per_device[k];
+  if (out) *out = R;
   return 0;
 }
 

@@ -44,12 +44,15 @@ namespace rt {
 struct PathArrays {
   float4* ray_o[2];  // origin.xyz, time                                    [2]: ping-pong sets, k_shade reads [parity], writes [parity ^ 1]
   float4* ray_d[2];  // direction.xyz, local pixel (int bits; < 0 = hole: no path at this position)
-  float4* thr[2];    // throughput.rgb, bounce (int bits)
-  float4* rad[2];    // radiance.rgb of the current sample, sample number (int bits)
+  float4* thr[2];    // throughput.rgb, bounce | sample number << 8 (int bits)
+                     // (no radiance in the state: of the reference's materials only diffuse_light emits and it never scatters
+                     //  (material.cuh:174-190), and a miss ends the path, so `radiance += throughput * emitted` (main.cu:71) is
+                     //  non-zero only in the event that ends the sample - it is computed and added to the pixel there)
   float2* hit;       // k_trace -> k_shade: t, packed hit (object | face << 25 | class << 28; -1 miss; -2 hole)
   float4* col;       // reference-RNG mode: float sum of the pixel's finished samples (per local pixel)
   uint32_t* rng;     // reference-RNG mode: 6 words per local pixel, SoA [6][n_slots]
   unsigned long long* acc64;  // Philox mode: per local pixel 3 x fixed-point (2^-32) radiance sums
+  unsigned long long* acc64_odd;  // adaptive sampling: the same sums over the ODD sample numbers only (error estimate), else null
   unsigned long long* next_work;  // Philox mode: next work item to hand out (shared by all pools)
   int* queues;       // [RT_NQ][subcap] positions of the dense layout, by (class, sub-queue)
   int subcap;
@@ -77,6 +80,8 @@ struct RenderParams {
   float tmin;            // 0.001f
   V3 background; int gradient;
   unsigned long long seed;  // 1984
+  const int* active;     // adaptive passes: the local pixels that still take samples (null: all rows_local * nx of them)
+  int n_active;
 };
 
 enum RngMode : int { RNG_PHILOX = 0, RNG_REFERENCE = 1 };
@@ -118,7 +123,7 @@ RT_D void rng_store(const Xorwow& g, const PathArrays& A, const RenderParams& P,
 }
 
 // New camera sample (main.cu:121-123): jitter, lens, shutter time; throughput 1, radiance 0. Written at position
-// `at` of ping-pong set `pp`; ray_d.w carries the local pixel, rad.w the sample number.
+// `at` of ping-pong set `pp`; ray_d.w carries the local pixel, thr.w bounce 0 and the sample number.
 template <class RNG>
 RT_D void start_sample(const DScene& S, const RenderParams& P, const PathArrays& A, int pp, int at, const SlotInfo& si, int sample, RNG& g) {
   const float u = fdiv(fadd((float)si.i, g.uniform()), (float)P.nx);
@@ -126,8 +131,7 @@ RT_D void start_sample(const DScene& S, const RenderParams& P, const PathArrays&
   const Ray r = camera_get_ray(S.cam, u, v, g);
   A.ray_o[pp][at] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
   A.ray_d[pp][at] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(si.lpix));
-  A.thr[pp][at] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
-  A.rad[pp][at] = make_float4(0.f, 0.f, 0.f, __int_as_float(sample));
+  A.thr[pp][at] = make_float4(1.f, 1.f, 1.f, __int_as_float(sample << 8));
 }
 RT_D void write_hole(const PathArrays& A, int pp, int at) { A.ray_d[pp][at] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); }
 
@@ -148,17 +152,18 @@ RT_D void fixed_add(unsigned long long* acc, float v) {
   atomicAdd(acc, (unsigned long long)__float2ll_rn(v * RT_FIXED_ONE));  // two's complement: negative values add correctly
 }
 RT_D void work_to_pixel_sample(const RenderParams& P, unsigned long long w, int& lpix, int& sample) {
+  const unsigned n_px = (unsigned)(P.active ? P.n_active : P.rows_local * P.nx);
   if (P.work_total <= 0xFFFFFFFFll) {  // the usual case: 32-bit divide
-    const unsigned npl = (unsigned)(P.rows_local * P.nx), w32 = (unsigned)w;
-    const unsigned s = w32 / npl;
-    lpix = (int)(w32 - s * npl);
+    const unsigned w32 = (unsigned)w;
+    const unsigned s = w32 / n_px;
+    lpix = (int)(w32 - s * n_px);
     sample = P.sample_base + (int)s;
   } else {
-    const unsigned long long npl = (unsigned long long)(P.rows_local * P.nx);
-    const unsigned long long s = w / npl;
-    lpix = (int)(w - s * npl);
+    const unsigned long long s = w / (unsigned long long)n_px;
+    lpix = (int)(w - s * n_px);
     sample = P.sample_base + (int)s;
   }
+  if (P.active) lpix = P.active[lpix];
 }
 
 // The first wave: position = slot. Philox mode: work item = work_base + slot (the host starts the work counter behind them);
@@ -326,14 +331,14 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
   if (live) {
     const int idx = A.queues[(size_t)qi * A.subcap + pos];
     const float4 o = A.ray_o[parity][idx], d = A.ray_d[parity][idx];
-    const float4 thr4 = A.thr[parity][idx], rad4 = A.rad[parity][idx];
+    const float4 thr4 = A.thr[parity][idx];
     const float2 hh = A.hit[idx];
     lpix = __float_as_int(d.w);
     const SlotInfo si = pixel_info(P, lpix);
     Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
-    V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(rad4.x, rad4.y, rad4.z);
-    int bounce = __float_as_int(thr4.w);
-    sample = __float_as_int(rad4.w);
+    V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(0.f, 0.f, 0.f);
+    int bounce = __float_as_int(thr4.w) & 255;
+    sample = __float_as_int(thr4.w) >> 8;
     rng_load(g, A, P, lpix, si.pix, sample, bounce + 1);
     bool sample_done;
     Ray nxt; nxt.o = r.o; nxt.d = r.d; nxt.tm = r.tm;
@@ -385,6 +390,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
         if (fabsf(rad.x) < RT_FIXED_MAX && fabsf(rad.y) < RT_FIXED_MAX && fabsf(rad.z) < RT_FIXED_MAX) {
           unsigned long long* acc = A.acc64 + 3 * (size_t)lpix;
           fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
+          if (A.acc64_odd && (sample & 1)) {
+            unsigned long long* ao = A.acc64_odd + 3 * (size_t)lpix;
+            fixed_add(ao + 0, rad.x); fixed_add(ao + 1, rad.y); fixed_add(ao + 2, rad.z);
+          }
         } else {
           atomicAdd(&C->nonfinite, 1u);
         }
@@ -393,8 +402,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
     } else {
       A.ray_o[po][gid] = make_float4(nxt.o.x, nxt.o.y, nxt.o.z, nxt.tm);
       A.ray_d[po][gid] = make_float4(nxt.d.x, nxt.d.y, nxt.d.z, d.w);
-      A.thr[po][gid] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce));
-      A.rad[po][gid] = make_float4(rad.x, rad.y, rad.z, rad4.w);
+      A.thr[po][gid] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce | (sample << 8)));
     }
   } else {
     write_hole(A, po, gid);
@@ -458,6 +466,47 @@ __global__ void k_accumulate(RenderParams P, PathArrays A, float* accum, int add
   }
   if (add) { x = fadd(accum[3 * lpix + 0], x); y = fadd(accum[3 * lpix + 1], y); z = fadd(accum[3 * lpix + 2], z); }
   accum[3 * lpix + 0] = x; accum[3 * lpix + 1] = y; accum[3 * lpix + 2] = z;
+}
+
+// ---- adaptive sampling ----
+// Error estimate of a TILE of tile x tile local pixels from two half-buffers (all samples / odd sample numbers):
+// mean over the tile's pixels of |I_even - I_odd|_1 / sqrt(|I_all|_1 + 1e-3)  (Dammertz et al. 2010).
+__global__ void k_tile_error(int nx, int rows, int tile, int tiles_x, const unsigned long long* acc, const unsigned long long* acc_odd,
+                             const int* n_even, const int* n_odd, float* err) {
+  const int t = blockIdx.x, tx = t % tiles_x, ty = t / tiles_x;
+  const double k = 1.0 / 4294967296.0;
+  const int ne = n_even[t], no = n_odd[t];
+  float sum = 0.f; int cnt = 0;
+  for (int q = threadIdx.x; q < tile * tile; q += blockDim.x) {
+    const int i = tx * tile + q % tile, j = ty * tile + q / tile;
+    if (i >= nx || j >= rows) continue;
+    const size_t p = 3 * ((size_t)j * nx + i);
+    float d = 0.f, a = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const double all = (double)(long long)acc[p + c] * k, odd = (double)(long long)acc_odd[p + c] * k;
+      const double io = no > 0 ? odd / no : 0.0, ie = ne > 0 ? (all - odd) / ne : 0.0;
+      d += (float)fabs(ie - io);
+      a += (float)fmax(all / (double)max(ne + no, 1), 0.0);
+    }
+    sum += d / sqrtf(a + 1e-3f);
+    ++cnt;
+  }
+  __shared__ float s_sum[256]; __shared__ int s_cnt[256];
+  s_sum[threadIdx.x] = sum; s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) { s_sum[threadIdx.x] += s_sum[threadIdx.x + w]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + w]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) err[t] = s_cnt[0] > 0 ? s_sum[0] / (float)s_cnt[0] : 0.f;
+}
+// accum (linear SUM over a pixel's samples) -> per-pixel MEAN: every tile has its own sample count
+__global__ void k_normalize_tiles(int nx, int rows, int tile, int tiles_x, const int* n_even, const int* n_odd, float* accum) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nx * rows) return;
+  const int i = p % nx, j = p / nx, t = (j / tile) * tiles_x + i / tile;
+  const float k = frcp((float)max(n_even[t] + n_odd[t], 1));
+  accum[3 * p + 0] = fmul(accum[3 * p + 0], k); accum[3 * p + 1] = fmul(accum[3 * p + 1], k); accum[3 * p + 2] = fmul(accum[3 * p + 2], k);
 }
 
 // fb = gamma(accum / ns) (main.cu:128-132). accum/fb are indexed by local pixel.

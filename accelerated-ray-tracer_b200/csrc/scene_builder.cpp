@@ -8,6 +8,7 @@
 //     Example: create_world_bouncing's camera v.y is 0.98894989490509 (folded) and not
 //     0.98894983530045 (fused). The `folded` flag selects this regime.
 #include "scene_builder.h"
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -239,6 +240,13 @@ int SceneBuilder::rotate_y(int obj, float angle_degrees) {  // hittable.cuh:89-1
   set_box(o, minp, maxp);
   return push_obj(o);
 }
+int SceneBuilder::with_material(int obj, int mat) {  // hittable.cuh:166-168: box = obj->bounding_box()
+  rt_object_desc o = obj_clear();
+  o.kind = RT_OBJ_WITH_MATERIAL; o.child = obj; o.mat = mat;
+  memcpy(o.box_min, S.obj[obj].box_min, 12);
+  memcpy(o.box_max, S.obj[obj].box_max, 12);
+  return push_obj(o);
+}
 int SceneBuilder::constant_medium_tex(int boundary, float density, int tex) {  // constant_medium.cuh:24-25
   rt_object_desc o = obj_clear();
   o.kind = RT_OBJ_MEDIUM; o.child = boundary;
@@ -392,9 +400,16 @@ std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* c
   }
   for (int i = 0; i < h.n_obj; ++i) {
     const rt_object_desc& o = sd.obj[i];
-    if (o.kind < RT_OBJ_SPHERE || o.kind > RT_OBJ_MEDIUM) return "object kind out of range";
+    if (o.kind < RT_OBJ_SPHERE || o.kind > RT_OBJ_WITH_MATERIAL) return "object kind out of range";
     const bool leaf = o.kind == RT_OBJ_SPHERE || o.kind == RT_OBJ_QUAD;
-    if ((leaf || o.kind == RT_OBJ_MEDIUM) && (o.mat < 0 || o.mat >= h.n_mat)) return "object material out of range";
+    if ((leaf || o.kind == RT_OBJ_MEDIUM || o.kind == RT_OBJ_WITH_MATERIAL) && (o.mat < 0 || o.mat >= h.n_mat)) return "object material out of range";
+    for (int a = 0; a < 3; ++a)
+      if (!std::isfinite(o.box_min[a]) || !std::isfinite(o.box_max[a])) return "object bounding box is not finite";
+    if (o.kind == RT_OBJ_SPHERE && !(std::isfinite(o.radius) && std::isfinite(o.c0[0]) && std::isfinite(o.c0[1]) && std::isfinite(o.c0[2]) &&
+                                     std::isfinite(o.dc[0]) && std::isfinite(o.dc[1]) && std::isfinite(o.dc[2]))) return "sphere is not finite";
+    if (o.kind == RT_OBJ_WITH_MATERIAL) {
+      if (o.child < 0 || o.child >= i) return "wrapper child must precede the wrapper";
+    }
     if (o.kind == RT_OBJ_BOX) {
       if (o.child < 0 || o.child + 6 > h.n_obj) return "box faces out of range";
       for (int f = 0; f < 6; ++f) if (sd.obj[o.child + f].kind != RT_OBJ_QUAD) return "box face is not a quad";
@@ -402,10 +417,12 @@ std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* c
     if (o.kind == RT_OBJ_TRANSLATE || o.kind == RT_OBJ_ROTATE_Y || o.kind == RT_OBJ_MEDIUM) {
       // children are created before their wrappers (like the reference's `new` order): no cycles, bounded depth
       if (o.child < 0 || o.child >= i) return "wrapper child must precede the wrapper";
-      if (sd.obj[o.child].kind == RT_OBJ_MEDIUM) return "a medium cannot be wrapped";
-      int depth = 0;
-      for (int c = i; sd.obj[c].kind == RT_OBJ_TRANSLATE || sd.obj[c].kind == RT_OBJ_ROTATE_Y || sd.obj[c].kind == RT_OBJ_MEDIUM; c = sd.obj[c].child)
-        if (sd.obj[c].kind != RT_OBJ_MEDIUM && ++depth > 4) return "more than 4 nested instance wrappers";
+      int depth = 0;  // material overrides vanish when the scene is flattened: they do not count
+      for (int c = i; sd.obj[c].kind == RT_OBJ_TRANSLATE || sd.obj[c].kind == RT_OBJ_ROTATE_Y || sd.obj[c].kind == RT_OBJ_MEDIUM ||
+                      sd.obj[c].kind == RT_OBJ_WITH_MATERIAL; c = sd.obj[c].child) {
+        if ((sd.obj[c].kind == RT_OBJ_TRANSLATE || sd.obj[c].kind == RT_OBJ_ROTATE_Y) && ++depth > 4) return "more than 4 nested instance wrappers";
+        if (c != i && sd.obj[c].kind == RT_OBJ_MEDIUM) return "a medium cannot be wrapped in an instance";
+      }
     }
   }
   for (int t : sd.top) if (t < 0 || t >= h.n_obj) return "top-level object out of range";

@@ -87,6 +87,7 @@ class SceneBuilder {
   int make_box(V3 a, V3 b, int mat);
   int translate(int obj, V3 offset);
   int rotate_y(int obj, float angle_degrees);
+  int with_material(int obj, int mat);  // hittable.cuh:154-178
   int constant_medium(int boundary, float density, V3 albedo);
   int constant_medium_tex(int boundary, float density, int tex);
 

@@ -52,9 +52,25 @@ class RenderStatsC(C.Structure):
                 ("profiled_waves", C.c_int32), ("trace_ms", C.c_double), ("shade_ms", C.c_double)]
 
 
+class AdaptiveParamsC(C.Structure):
+    _fields_ = [("min_spp", C.c_int32), ("max_spp", C.c_int32), ("pass_spp", C.c_int32), ("tile", C.c_int32),
+                ("threshold", C.c_float), ("reserved", C.c_int32 * 3)]
+
+
+class AdaptiveStatsC(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("device_ms", C.c_double), ("passes", C.c_int32),
+                ("tiles", C.c_int32), ("tiles_converged", C.c_int32), ("min_spp_used", C.c_int32), ("max_spp_used", C.c_int32),
+                ("mean_spp", C.c_float), ("err_min", C.c_float), ("err_max", C.c_float), ("err_spp", C.c_int32)]
+
+
+class QueueStatsC(C.Structure):
+    _fields_ = [("n_chunks", C.c_int32), ("chunks_per_device", C.c_int32 * 16), ("device_ms", C.c_double * 16),
+                ("rays_per_device", C.c_uint64 * 16), ("rays", C.c_uint64)]
+
+
 EXPORTS = ["rt_build_scene", "rt_build_scene_sd", "rt_render", "rt_render_stats_get", "rt_readback", "rt_readback_t", "rt_destroy",
            "rt_last_error", "rt_scene_info_get", "rt_scene_export", "rt_scene_export_host", "rt_accum_device_ptr",
-           "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm", "rt_load_texture", "rt_write_image", "rt_accum_reduce"]
+           "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm", "rt_load_texture", "rt_write_image", "rt_accum_reduce", "rt_render_adaptive", "rt_readback_spp", "rt_render_queue"]
 
 _lib = None
 
@@ -88,6 +104,9 @@ def lib():
         L.rt_write_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.rt_write_image.restype = C.c_long
         L.rt_accum_reduce.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
+        L.rt_render_adaptive.argtypes = [C.c_void_p, C.POINTER(RenderParamsC), C.POINTER(AdaptiveParamsC), C.POINTER(AdaptiveStatsC)]
+        L.rt_readback_spp.argtypes = [C.c_void_p, C.c_void_p]
+        L.rt_render_queue.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(RenderParamsC), C.c_int32, C.c_void_p, C.POINTER(QueueStatsC)]
         L.rt_load_texture.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
@@ -183,6 +202,8 @@ class SD:
             return ("felt", self._f(d["color"]), self._f(d["p"][:4]))
         if k == 6:
             return ("uv_offset", self._f(d["p"][:2]), self.tex_key(int(d["even"])))
+        if k == 6:
+            return ("with_material", self.obj_key(int(d["child"]), with_box), self.mat_key(int(d["mat"])), box)
         return ("?", k)
 
     def mat_key(self, m):
@@ -308,6 +329,32 @@ class Scene:
         self._world, self._rank, self._split = world, rank, split_mode
         return st
 
+    def render_adaptive(self, max_spp, threshold, min_spp=0, pass_spp=16, tile=16, rank=0, world=1, seed=0, slots=0,
+                        max_depth=0, gamma=0.0, background=None, gradient_bg=None):
+        """Adaptive per-tile sampling (rt_render_adaptive): returns AdaptiveStatsC; framebuffer() / spp_map() afterwards."""
+        p = RenderParamsC()
+        p.spp, p.max_depth, p.gamma = max_spp, max_depth, gamma
+        if background is not None:
+            p.override_background = 1
+            p.background[0], p.background[1], p.background[2] = background
+            p.gradient_bg = int(bool(gradient_bg))
+        p.seed, p.rng_mode, p.split_mode, p.rank, p.world, p.slots = seed, 0, 0, rank, world, slots
+        a = AdaptiveParamsC(min_spp, max_spp, pass_spp, tile, threshold)
+        out = AdaptiveStatsC()
+        _check(lib().rt_render_adaptive(self._h, C.byref(p), C.byref(a), C.byref(out)))
+        st = RenderStatsC()
+        _check(lib().rt_render_stats_get(self._h, C.byref(st)))
+        self.stats = st
+        self._world, self._rank, self._split = world, rank, 0
+        return out
+
+    def spp_map(self):
+        """Samples every pixel of this rank's share received in the last adaptive render: int32 (rows_local, nx)."""
+        st = self.stats
+        m = np.empty((st.rows_local, st.nx), dtype=np.int32)
+        _check(lib().rt_readback_spp(self._h, m.ctypes.data))
+        return m
+
     def framebuffer(self):
         """This rank's share: float32 (rows_local, nx, 3), gamma applied, local row 0 = lowest owned scanline."""
         st = self.stats
@@ -345,6 +392,21 @@ class Scene:
         rank = np.zeros(self.info.n_top, dtype=np.int32)
         _check(L.rt_scene_export(self._h, buf, need.value, C.byref(need), rank.ctypes.data))
         return SD(bytes(buf)), rank
+
+
+def render_queue(scenes, spp, n_chunks=0, rng_mode=0, seed=0, max_depth=0, background=None, gradient_bg=None):
+    """Dynamic tile queue over scene replicas of this process (rt_render_queue): returns (full (ny, nx, 3) image, QueueStatsC)."""
+    p = RenderParamsC()
+    p.spp, p.rng_mode, p.seed, p.max_depth = spp, rng_mode, seed, max_depth
+    if background is not None:
+        p.override_background = 1
+        p.background[0], p.background[1], p.background[2] = background
+        p.gradient_bg = int(bool(gradient_bg))
+    arr = (C.c_void_p * len(scenes))(*[sc._h for sc in scenes])
+    out = np.zeros((scenes[0].ny, scenes[0].nx, 3), dtype=np.float32)
+    st = QueueStatsC()
+    _check(lib().rt_render_queue(arr, len(scenes), C.byref(p), n_chunks, out.ctypes.data, C.byref(st)))
+    return out, st
 
 
 def assemble_rows(parts, ny):

@@ -99,6 +99,46 @@ def gather_rows_to_root(t_local, ny, root=0):
     return out
 
 
+_queue_epoch = [0]
+
+
+def next_chunk(key, n_chunks):
+    """Cross-process dynamic tile queue: an atomic counter in the process group's key-value store (TCPStore.add is
+    atomic); returns the next unclaimed chunk id or None when all n_chunks are taken."""
+    import torch.distributed as dist
+    store = dist.distributed_c10d._get_default_store()
+    c = int(store.add(key, 1)) - 1
+    return c if c < n_chunks else None
+
+
+def render_dynamic(scene_render, n_chunks, ny, nx, device=None):
+    """Dynamic tile queue across the ranks of the process group. The image is cut into n_chunks tile shares
+    (share c = scanlines j = c mod n_chunks); every rank pulls share ids from a shared counter and calls
+    scene_render(c, n_chunks) -> (rows_c, nx, 3) tensor until none is left, writing the rows into its own zero-initialised
+    full image; one reduce-sum to rank 0 then merges them (every row is written by exactly one rank and x + 0 is exact, so
+    the result is bit-identical to a single-GPU render). Returns (full image on rank 0 else None, chunk ids this rank rendered)."""
+    import torch
+    import torch.distributed as dist
+    multi = dist.is_initialized() and dist.get_world_size() > 1
+    _queue_epoch[0] += 1
+    key = "rt_tile_queue_%d" % _queue_epoch[0]
+    full = torch.zeros((ny, nx, 3), dtype=torch.float32, device=device)
+    mine = []
+    c = 0
+    while True:
+        c = next_chunk(key, n_chunks) if multi else (len(mine) if len(mine) < n_chunks else None)
+        if c is None:
+            break
+        rows = scene_render(c, n_chunks)
+        full[c::n_chunks] = rows.to(full.device).view(-1, nx, 3)
+        mine.append(c)
+    if multi:
+        dist.reduce(full, dst=0, op=dist.ReduceOp.SUM)
+        if dist.get_rank() != 0:
+            return None, mine
+    return full, mine
+
+
 # ---- device-side helpers (library-owned buffers as torch tensors, zero copy) ----
 def accum_tensor(scene):
     """This rank's linear per-pixel radiance sums (rows_local*nx*3 floats) as a CUDA tensor view."""

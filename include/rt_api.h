@@ -76,6 +76,27 @@ typedef struct rt_render_stats {
   double trace_ms, shade_ms; /* summed device time of the k_trace / k_shade launches */
 } rt_render_stats;
 
+/* Adaptive per-tile sampling (the step after the reference's fixed `for s < ns` loop, main.cu:119): passes of pass_spp
+ * samples; after each pass every still-active tile's error is estimated from two half-buffers and tiles below `threshold`
+ * stop. threshold <= 0: nothing ever stops (the result then equals rt_render(spp = max_spp) bit for bit). */
+typedef struct rt_adaptive_params {
+  int32_t min_spp;         /* no tile stops before this many samples per pixel (at least one pass) */
+  int32_t max_spp;         /* <= 0: rt_render_params.spp, else the scene function's own value */
+  int32_t pass_spp;        /* samples per pixel per pass (even; <= 0: 16) */
+  int32_t tile;            /* tile edge in pixels (<= 0: 16) */
+  float threshold;         /* mean over the tile of |I_even - I_odd|_1 / sqrt(|I|_1 + 1e-3), linear radiance */
+  int32_t reserved[3];
+} rt_adaptive_params;
+typedef struct rt_adaptive_stats {
+  uint64_t samples, rays;
+  double device_ms;
+  int32_t passes, tiles, tiles_converged;
+  int32_t min_spp_used, max_spp_used;
+  float mean_spp;
+  float err_min, err_max;  /* smallest / largest tile error of the last estimate (over the tiles active at that time) */
+  int32_t err_spp;         /* samples per pixel those tiles had when it was taken */
+} rt_adaptive_stats;
+
 /* create_world_*<<<1,1>>> + texture upload (main.cu:1186-1204): host generator -> H2D -> device BVH build. */
 int rt_build_scene(const rt_scene_desc* desc, rt_scene** out);
 /* The same from a caller-made scene: `sd` is a scene description in the flat format of rt_scene_desc.h (what the
@@ -88,6 +109,10 @@ int rt_build_scene_sd(const void* sd, size_t sd_bytes, const unsigned char* cons
 /* render_init + render (main.cu:1207-1209). device_ms / rays may be NULL. */
 int rt_render(rt_scene* s, const rt_render_params* p, double* device_ms, uint64_t* rays);
 int rt_render_stats_get(rt_scene* s, rt_render_stats* out);
+/* Counter-based RNG, tile split only. Leaves the framebuffer resolved (per-pixel mean, gamma) and the accumulation buffer
+ * holding per-pixel MEANS; rt_readback_spp returns the samples each pixel of this rank's share received. */
+int rt_render_adaptive(rt_scene* s, const rt_render_params* p, const rt_adaptive_params* a, rt_adaptive_stats* out);
+int rt_readback_spp(rt_scene* s, int32_t* spp);
 /* The managed-memory framebuffer read (main.cu:1212-1221). rgb: rows_local*nx*3 floats, gamma applied,
  * local row lr is image row j = lr*world + rank, j = 0 is the BOTTOM scanline like the reference's fb.
  * obj_id / mat_id / t (each rows_local*nx, nullable) need aov != 0 in the last rt_render. */
@@ -114,6 +139,20 @@ int rt_resolve(rt_scene* s, int32_t total_spp, float gamma); /* accum -> framebu
  * NVLink when peer access is available, else through one cudaMemcpyPeerAsync each. Then rt_resolve(dst, total spp).
  * (Across processes the same sum is an NCCL reduce on rt_accum_device_ptr, see pyrt/dist.py.) */
 int rt_accum_reduce(rt_scene* dst, rt_scene* const* src, int32_t n_src);
+/* Dynamic tile queue inside ONE process: scenes[] = replicas of the same scene (normally one per device; several on one
+ * device also work), each driven by its own host thread that pulls the next of n_chunks tile shares (interleaved
+ * scanlines, n_chunks <= 0: 8 per replica) from a shared counter, renders it and copies its rows into rgb_full
+ * (ny*nx*3 floats, host). Load-balances unequal GPUs / unequal rows; the image does not depend on who rendered what. */
+#define RT_QUEUE_MAX_DEVICES 16
+typedef struct rt_queue_stats {
+  int32_t n_chunks;
+  int32_t chunks_per_device[RT_QUEUE_MAX_DEVICES];
+  double device_ms[RT_QUEUE_MAX_DEVICES];
+  uint64_t rays_per_device[RT_QUEUE_MAX_DEVICES];
+  uint64_t rays;
+} rt_queue_stats;
+int rt_render_queue(rt_scene* const* scenes, int32_t n_scenes, const rt_render_params* p, int32_t n_chunks, float* rgb_full,
+                    rt_queue_stats* out);
 /* Device address of this rank's framebuffer share (rows_local*nx*3 floats), e.g. for an NCCL gather of tiles. */
 int rt_fb_device_ptr(rt_scene* s, void** dptr, size_t* n_floats);
 

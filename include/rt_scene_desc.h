@@ -70,12 +70,15 @@ enum rt_obj_kind {
   RT_OBJ_BOX = 2,       /* compound6 from make_box, quad.cuh:94-162; child = first of 6 quads */
   RT_OBJ_TRANSLATE = 3, /* hittable.cuh:40-69                                      */
   RT_OBJ_ROTATE_Y = 4,  /* hittable.cuh:77-149                                     */
-  RT_OBJ_MEDIUM = 5     /* constant_medium.cuh:17-79; child = boundary, mat = phase function */
+  RT_OBJ_MEDIUM = 5,    /* constant_medium.cuh:17-79; child = boundary, mat = phase function */
+  RT_OBJ_WITH_MATERIAL = 6 /* with_material(obj, mat), hittable.cuh:154-178: child's geometry and box, every hit reports
+                              `mat` (the OUTERMOST override wins: each wrapper sets rec.mat_ptr after its child's hit) */
 };
 
 typedef struct rt_object_desc {
   int32_t kind;
-  int32_t mat;        /* sphere/quad: material; box: material of face 0; medium: isotropic phase material */
+  int32_t mat;        /* sphere/quad: material; box: material of face 0; medium: isotropic phase material;
+                         with_material: the override */
   int32_t child;      /* wrapper: wrapped object; box: id of face 0 (faces are child..child+5) */
   int32_t inward;     /* quad only */
   float c0[3];        /* sphere: center.A */

@@ -261,6 +261,10 @@ bool object_hit(const Scene& S, int o, const ray& r, float tmin, float tmax, hit
       return true;
     }
     case RT_OBJ_MEDIUM: return medium_hit(S, d, r, tmin, tmax, rec);
+    case RT_OBJ_WITH_MATERIAL:  // hittable.cuh:170-174
+      if (!object_hit(S, d.child, r, tmin, tmax, rec)) return false;
+      rec.mat = d.mat;
+      return true;
   }
   return false;
 }

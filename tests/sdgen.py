@@ -107,6 +107,11 @@ class SDBuilder:
         o["box_min"], o["box_max"] = self.obj[boundary]["box_min"], self.obj[boundary]["box_max"]
         return self._push(o)
 
+    def with_material(self, child, mat):
+        o = self._obj(6); o["child"] = child; o["mat"] = mat
+        o["box_min"], o["box_max"] = self.obj[child]["box_min"], self.obj[child]["box_max"]
+        return self._push(o)
+
     def add(self, o): self.top.append(o)
 
     def camera(self, lookfrom, lookat, vup, vfov, aperture, focus, t0=0.0, t1=1.0):
@@ -130,7 +135,7 @@ class SDBuilder:
                 b"".join(o.tobytes() for o in self.obj) + np.asarray(self.top, "<i4").tobytes())
 
 
-def random_scene(seed, nx=160, ny=120, n_spheres=60, n_boxes=12, media=True):
+def random_scene(seed, nx=160, ny=120, n_spheres=60, n_boxes=12, media=True, overrides=False):
     """A room of random primitives that exercises every hittable / material branch, including the reference's odd
     corners: negative-radius spheres (hollow glass), moving spheres, nested translate(rotate_y(box)), media whose
     boundary is a sphere or an instanced box, objects that touch and overlap."""
@@ -162,6 +167,20 @@ def random_scene(seed, nx=160, ny=120, n_spheres=60, n_boxes=12, media=True):
         if kind == 2 or rng.random() < 0.8:
             bx = B.translate(bx, rng.uniform((-8, 0, -8), (8, 4, 8)))
         B.add(bx)
+    if overrides:
+        # with_material (hittable.cuh:154-178): shared geometry, per-instance look. One sphere and one box reused under
+        # different materials; override of an instanced box, instance of an overridden box, override on top of an
+        # override (the outermost wins), and an overridden medium (the phase function is replaced)
+        ball = B.sphere((0, 0, 0), 0.8, mats[0])
+        crate = B.box((0, 0, 0), (1.2, 1.8, 1.2), mats[1])
+        for k in range(6):
+            off = rng.uniform((-8, 0.8, -8), (8, 5, 8))
+            B.add(B.translate(B.with_material(ball, mats[(3 + k) % len(mats)]), off))
+        B.add(B.with_material(B.translate(B.rotate_y(crate, 30.0), (-3, 0, 5)), mats[3]))
+        B.add(B.translate(B.rotate_y(B.with_material(crate, mats[7]), -20.0), (4, 0, 6)))
+        B.add(B.with_material(B.with_material(B.translate(crate, (0, 0, 7)), mats[4]), mats[6]))
+        if media:
+            B.add(B.with_material(B.medium(B.sphere((-4, 2, -3), 1.5, mats[5]), 0.8, white), B.isotropic(red)))
     if media:
         B.add(B.medium(B.sphere((3, 3, 0), 2.0, mats[5]), 0.4, B.solid((0.2, 0.4, 0.9))))
         B.add(B.medium(B.translate(B.rotate_y(B.box((0, 0, 0), (2.5, 2.5, 2.5), mats[0]), 25.0), (-6, 0.5, 2)), 0.3, white))

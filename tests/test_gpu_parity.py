@@ -227,6 +227,70 @@ def test_edge_cases(pyrt):
         pyrt.Scene(3, 8, 8, texture_dir="/nonexistent")  # missing texture is an error, not the cyan fallback
 
 
+def test_dynamic_tile_queue_is_bit_identical(pyrt):
+    """rt_render_queue: tile shares handed out at run time to whichever replica is free (here two replicas on the one GPU,
+    each with its own host thread) give the same bits as one plain render, in both RNG modes, whatever the share count."""
+    for rng_mode in (0, 1):
+        with _scene(pyrt, 1, 160, 90) as a, _scene(pyrt, 1, 160, 90) as b:
+            a.render(spp=4, rng_mode=rng_mode)
+            whole = a.framebuffer()
+            for n_chunks in (0, 5, 90, 1000):
+                img, st = pyrt.render_queue([a, b], spp=4, n_chunks=n_chunks, rng_mode=rng_mode)
+                assert np.array_equal(img.view(np.uint32), whole.view(np.uint32)), (rng_mode, n_chunks)
+                assert st.n_chunks == (16 if n_chunks == 0 else min(n_chunks, 90))
+                assert st.chunks_per_device[0] + st.chunks_per_device[1] == st.n_chunks and st.rays > 0
+    with _scene(pyrt, 7, 32, 32) as a, _scene(pyrt, 7, 48, 32) as b:
+        with pytest.raises(pyrt.RtError, match="differ in resolution"):
+            pyrt.render_queue([a, b], spp=1)
+
+
+def test_adaptive_sampling(pyrt):
+    """Adaptive per-tile spp. (1) With a threshold nothing meets, every tile runs every pass and the image is
+    bit-identical to the plain render of max_spp samples (same sample numbers, order-free fixed-point sums). (2) With a
+    real threshold smooth tiles stop early, noisy ones run on: fewer samples than uniform for an image at least as close
+    to a converged render as the uniform render of the SAME total sample count (north_star tolerance checked on both:
+    mean error <= 1/255 per channel against the 4096-spp image)."""
+    with _scene(pyrt, 7, 128, 128) as sc:
+        sc.render(spp=64, rng_mode=0)
+        plain = sc.framebuffer()
+        a = sc.render_adaptive(max_spp=64, threshold=0.0, pass_spp=16, tile=16)
+        assert a.passes == 4 and a.tiles == 64 and a.tiles_converged == 0 and a.samples == 128 * 128 * 64
+        assert np.array_equal(sc.framebuffer().view(np.uint32), plain.view(np.uint32))
+        assert (sc.spp_map() == 64).all()
+        sc.render(spp=4096, rng_mode=0, seed=77)
+        conv = sc.framebuffer()
+        # threshold from a probe: the tile errors after 96 spp span [err_min, err_max] and fall like 1/sqrt(n); aim the
+        # threshold at the geometric middle of that range as it will look at 256 spp
+        probe = sc.render_adaptive(max_spp=128, threshold=0.0, pass_spp=32, tile=16)
+        assert probe.err_spp == 96 and 0 < probe.err_min < probe.err_max
+        thr = float(np.sqrt(probe.err_min * probe.err_max) * np.sqrt(96.0 / 256.0))
+        a = sc.render_adaptive(max_spp=1024, threshold=thr, min_spp=32, pass_spp=32, tile=16)
+        ad = sc.framebuffer()
+        m = sc.spp_map()
+        print("adaptive: %d passes, %d/%d tiles converged, spp %d..%d mean %.1f" %
+              (a.passes, a.tiles_converged, a.tiles, a.min_spp_used, a.max_spp_used, a.mean_spp))
+        assert a.min_spp_used >= 32 and a.max_spp_used <= 1024 and a.min_spp_used < a.max_spp_used
+        assert 0 < a.tiles_converged <= a.tiles and a.samples == int(m.sum())
+        assert a.mean_spp < 0.95 * 1024
+        uni_spp = int(round(a.mean_spp / 2)) * 2
+        sc.render(spp=uni_spp, rng_mode=0)
+        uni = sc.framebuffer()
+    err_ad, err_uni = _psnr(ad, conv), _psnr(uni, conv)
+    print("PSNR vs 4096 spp: adaptive %.2f dB (%.1f spp mean), uniform %.2f dB (%d spp)" % (err_ad, a.mean_spp, err_uni, uni_spp))
+    assert err_ad >= err_uni - 0.5
+    for img in (ad, uni):
+        assert float(np.abs(np.clip(img, 0, 1).mean(axis=(0, 1)) - np.clip(conv, 0, 1).mean(axis=(0, 1))).max()) <= 1.0 / 255.0
+    with _scene(pyrt, 7, 64, 64) as sc:
+        with pytest.raises(pyrt.RtError):
+            sc.render_adaptive(max_spp=64, threshold=0.1, world=2, rank=5)   # rank out of range
+        a = sc.render_adaptive(max_spp=40, threshold=0.0, pass_spp=16, tile=24, world=3, rank=1)   # ragged tiles, a tile-split share
+        assert a.passes == 3 and sc.framebuffer().shape == (21, 64, 3) and (sc.spp_map() == 40).all()
+        sc.render(spp=40, rng_mode=0, world=3, rank=1)
+        ref = sc.framebuffer()
+        sc.render_adaptive(max_spp=40, threshold=0.0, pass_spp=16, tile=24, world=3, rank=1)
+        assert np.array_equal(sc.framebuffer().view(np.uint32), ref.view(np.uint32))
+
+
 def test_philox_is_deterministic_and_seed_dependent(pyrt):
     with _scene(pyrt, 8, 96, 96) as sc:
         sc.render(spp=8, rng_mode=0)
@@ -324,8 +388,8 @@ def test_cli_ppm_on_stdout_matches_reference_image(pyrt, golden, built):
     assert bad.returncode == 99 and "unknown scene" in bad.stderr
 
 
-@pytest.mark.parametrize("seed,media", [(1, False), (2, True), (3, True), (4, False)])
-def test_random_scene_matches_oracle(pyrt, built, seed, media):
+@pytest.mark.parametrize("seed,media,overrides", [(1, False, False), (2, True, False), (3, True, True), (4, False, True)])
+def test_random_scene_matches_oracle(pyrt, built, seed, media, overrides):
     """The generic path (rt_build_scene_sd) on random scenes built from the whole vocabulary - moving and negative-radius
     spheres, quads, boxes under translate(rotate_y()), media with sphere and instanced-box boundaries - against the CPU
     oracle on the same bytes: primary-hit object / material bit-exact, t bit-exact (inside a medium: logf, 1e-5),
@@ -335,7 +399,7 @@ def test_random_scene_matches_oracle(pyrt, built, seed, media):
     import oracle_py
     from sdgen import random_scene
     nx, ny, spp = 160, 120, 4
-    sd = random_scene(seed, nx, ny, media=media)
+    sd = random_scene(seed, nx, ny, media=media, overrides=overrides)   # overrides: with_material wrappers (hittable.cuh:154-178)
     o = oracle_py.Oracle(sd)
     o_obj, o_mat, o_t = o.primary_ids(nx, ny)
     o_fb, o_rays = o.render(nx, ny, spp, background=(0.02, 0.03, 0.05))
@@ -348,7 +412,12 @@ def test_random_scene_matches_oracle(pyrt, built, seed, media):
         fb2 = sc.framebuffer()
     assert np.array_equal(obj, o_obj) and np.array_equal(mat, o_mat)
     parsed = pyrt.SD(sd)
-    is_medium = (obj >= 0) & (parsed.obj["kind"][parsed.top][np.maximum(obj, 0)] == 5)
+    def _is_medium(o):  # a medium, possibly under material overrides
+        while int(parsed.obj["kind"][o]) == 6:
+            o = int(parsed.obj["child"][o])
+        return int(parsed.obj["kind"][o]) == 5
+    top_is_medium = np.array([_is_medium(int(o)) for o in parsed.top])
+    is_medium = (obj >= 0) & top_is_medium[np.maximum(obj, 0)]
     assert np.array_equal(t.view(np.uint32)[~is_medium], o_t.view(np.uint32)[~is_medium])
     assert np.allclose(t[is_medium], o_t[is_medium], rtol=1e-5, atol=0)
     close = float((np.abs(fb - o_fb) <= 2e-5).all(axis=2).mean())

@@ -36,7 +36,7 @@ def test_struct_layouts_match_header(pyrt):
 #include "rt_scene_desc.h"
 int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rt_scene_desc), sizeof(rt_render_params),
   sizeof(rt_scene_info), sizeof(rt_render_stats), sizeof(rt_texture_desc), sizeof(rt_material_desc), sizeof(rt_object_desc),
-  sizeof(rt_camera_desc), sizeof(rt_sd_header)); return 0; }
+  sizeof(rt_camera_desc), sizeof(rt_sd_header)); printf("%zu %zu %zu\n", sizeof(rt_adaptive_params), sizeof(rt_adaptive_stats), sizeof(rt_queue_stats)); return 0; }
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -45,7 +45,8 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rt_scene
         out = subprocess.check_output([os.path.join(d, "t")]).split()
     sizes = [int(x) for x in out]
     assert sizes[:4] == [C.sizeof(pyrt.SceneDescC), C.sizeof(pyrt.RenderParamsC), C.sizeof(pyrt.SceneInfoC), C.sizeof(pyrt.RenderStatsC)]
-    assert sizes[4:] == [pyrt.TEX_DT.itemsize, pyrt.MAT_DT.itemsize, pyrt.OBJ_DT.itemsize, pyrt.CAM_DT.itemsize, pyrt.HDR_DT.itemsize]
+    assert sizes[4:9] == [pyrt.TEX_DT.itemsize, pyrt.MAT_DT.itemsize, pyrt.OBJ_DT.itemsize, pyrt.CAM_DT.itemsize, pyrt.HDR_DT.itemsize]
+    assert sizes[9:] == [C.sizeof(pyrt.AdaptiveParamsC), C.sizeof(pyrt.AdaptiveStatsC), C.sizeof(pyrt.QueueStatsC)]
 
 
 JPEG_DIR = os.path.join(ROOT, "oracle", "_ref", "textures_jpg")
@@ -263,6 +264,24 @@ acc = torch.full((ny * nx * 3,), float(end - base))
 dist.reduce_sum_to_root(acc)
 if rank == 0:
     assert torch.all(acc == 10.0)
+# dynamic tile queue: 7 chunks pulled from the shared counter by 2 ranks; rank 1 is "slow" and must end up with fewer
+import time
+def fake_render(c, n):
+    if rank == 1:
+        time.sleep(0.05)
+    return full[c::n].contiguous()
+img, mine = dist.render_dynamic(fake_render, 7, ny, nx)
+counts = [None, None]
+td.all_gather_object(counts, mine)
+assert sorted(counts[0] + counts[1]) == list(range(7)), counts
+assert len(counts[0]) > len(counts[1]) >= 0, counts
+if rank == 0:
+    assert torch.equal(img, full)
+else:
+    assert img is None
+img2, mine2 = dist.render_dynamic(fake_render, 3, ny, nx)   # a second queue in the same group gets a fresh counter
+td.all_gather_object(counts, mine2)
+assert sorted(counts[0] + counts[1]) == [0, 1, 2]
 td.barrier()
 td.destroy_process_group()
 print("rank %%d ok" %% rank)
