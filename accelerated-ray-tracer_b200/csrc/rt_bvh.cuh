@@ -142,6 +142,24 @@ __global__ void k_ploc_init(const BuildBox* boxes, const int* sorted, int n, int
 // Ties are broken by a total order on PAIRS (even left position first, then the smaller left position), which
 // (a) guarantees a mutual pair every round and (b) pairs a run of equidistant clusters as (0,1)(2,3)(4,5)...
 // instead of merging one pair per round into a chain: regular grids (the C5 sphere grid) are full of such runs.
+// The search of one cluster i over its neighbours' boxes (box_of(j) for j in [i - R, i + R]).
+template <class BoxOf>
+RT_D int ploc_nearest(int i, int m, BoxOf box_of) {
+  const BuildBox a = box_of(i);
+  float best = FLT_MAX; int bj = -1; unsigned bkey = 0xFFFFFFFFu;
+  for (int d = -RT_PLOC_RADIUS; d <= RT_PLOC_RADIUS; ++d) {
+    const int j = i + d;
+    if (d == 0 || j < 0 || j >= m) continue;
+    const BuildBox b = box_of(j);
+    BuildBox u;
+    for (int x = 0; x < 3; ++x) { u.mn[x] = fminf(a.mn[x], b.mn[x]); u.mx[x] = fmaxf(a.mx[x], b.mx[x]); }
+    const float ar = box_area(u);
+    const unsigned lft = (unsigned)min(i, j);
+    const unsigned key = ((lft & 1u) << 31) | lft;  // the right partner is then fixed by the distance |d|: ascending |d| below
+    if (ar < best || (ar == best && (key < bkey || (key == bkey && abs(d) < abs(bj - i))))) { best = ar; bj = j; bkey = key; }
+  }
+  return bj;
+}
 __global__ void __launch_bounds__(RT_PLOC_BLOCK) k_ploc_nn(const int* cl, int m, const BuildBox* nbox, int* nn) {
   __shared__ BuildBox sb[RT_PLOC_BLOCK + 2 * RT_PLOC_RADIUS];
   const int start = blockIdx.x * RT_PLOC_BLOCK - RT_PLOC_RADIUS;
@@ -152,20 +170,7 @@ __global__ void __launch_bounds__(RT_PLOC_BLOCK) k_ploc_nn(const int* cl, int m,
   __syncthreads();
   const int i = blockIdx.x * RT_PLOC_BLOCK + threadIdx.x;
   if (i >= m) return;
-  const BuildBox a = sb[threadIdx.x + RT_PLOC_RADIUS];
-  float best = FLT_MAX; int bj = -1; unsigned bkey = 0xFFFFFFFFu;
-  for (int d = -RT_PLOC_RADIUS; d <= RT_PLOC_RADIUS; ++d) {
-    const int j = i + d;
-    if (d == 0 || j < 0 || j >= m) continue;
-    const BuildBox b = sb[threadIdx.x + RT_PLOC_RADIUS + d];
-    BuildBox u;
-    for (int x = 0; x < 3; ++x) { u.mn[x] = fminf(a.mn[x], b.mn[x]); u.mx[x] = fmaxf(a.mx[x], b.mx[x]); }
-    const float ar = box_area(u);
-    const unsigned lft = (unsigned)min(i, j);
-    const unsigned key = ((lft & 1u) << 31) | lft;  // the right partner is then fixed by the distance |d|: ascending |d| below
-    if (ar < best || (ar == best && (key < bkey || (key == bkey && abs(d) < abs(bj - i))))) { best = ar; bj = j; bkey = key; }
-  }
-  nn[i] = bj;
+  nn[i] = ploc_nearest(i, m, [&](int j) { return sb[j - start]; });
 }
 // Mutual nearest neighbours merge into a new interior node that takes the place of the LEFT partner.
 __global__ void k_ploc_merge(const int* cl, int m, const int* nn, BuildBox* nbox, int* left, int* right, int* next_id, int* cl_out) {
@@ -191,13 +196,71 @@ __global__ void k_ploc_merge(const int* cl, int m, const int* nn, BuildBox* nbox
 }
 struct PlocAlive { __device__ bool operator()(int v) const { return v >= 0; } };
 
+// Scenes of up to RT_PLOC_SMALL objects (every scene function of the reference: 8 .. 1409): ALL rounds in one CTA, the
+// cluster array in shared memory, block-wide scan for the compaction - one launch instead of ~40 rounds x (3 kernels + a
+// host read of the cluster count). Same search, same tie rules, same merge as the kernels above.
+#define RT_PLOC_SMALL 2048
+#define RT_PLOC_SMALL_THREADS 1024
+__global__ void __launch_bounds__(RT_PLOC_SMALL_THREADS) k_ploc_small(const BuildBox* boxes, const int* sorted, int n, BuildBox* nbox,
+                                                                      int* left, int* right, int* root_out) {
+  __shared__ int cl[2][RT_PLOC_SMALL];
+  __shared__ int nn[RT_PLOC_SMALL];
+  __shared__ int s_next, s_m;
+  typedef cub::BlockScan<int, RT_PLOC_SMALL_THREADS> Scan;
+  __shared__ typename Scan::TempStorage scan_tmp;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < n; k += RT_PLOC_SMALL_THREADS) { cl[0][k] = n - 1 + k; nbox[n - 1 + k] = boxes[sorted[k]]; }
+  if (tid == 0) { s_next = 0; s_m = n; }
+  __syncthreads();
+  int cur = 0;
+  while (true) {
+    const int m = s_m;
+    if (m <= 1) break;
+    for (int i = tid; i < m; i += RT_PLOC_SMALL_THREADS) nn[i] = ploc_nearest(i, m, [&](int j) { return nbox[cl[cur][j]]; });
+    __syncthreads();
+    int out[2] = {-1, -1};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = 2 * tid + q;  // two consecutive clusters per thread: the scan below keeps their order
+      if (i >= m) continue;
+      const int j = nn[i];
+      out[q] = cl[cur][i];
+      if (j >= 0 && nn[j] == i) {
+        if (i < j) {
+          const int id = atomicAdd(&s_next, 1);
+          const int l = cl[cur][i], r = cl[cur][j];
+          left[id] = l; right[id] = r;
+          const BuildBox a = nbox[l], b = nbox[r];
+          BuildBox u;
+          for (int x = 0; x < 3; ++x) { u.mn[x] = fminf(a.mn[x], b.mn[x]); u.mx[x] = fmaxf(a.mx[x], b.mx[x]); }
+          nbox[id] = u;
+          out[q] = id;
+        } else {
+          out[q] = -1;  // absorbed by its partner
+        }
+      }
+    }
+    const int alive = (out[0] >= 0) + (out[1] >= 0);
+    int pos, total;
+    Scan(scan_tmp).ExclusiveSum(alive, pos, total);
+    if (out[0] >= 0) cl[cur ^ 1][pos++] = out[0];
+    if (out[1] >= 0) cl[cur ^ 1][pos] = out[1];
+    __syncthreads();  // also orders the nbox / left / right writes before the next round's reads
+    if (tid == 0) s_m = total;
+    cur ^= 1;
+    __syncthreads();
+  }
+  if (tid == 0) *root_out = cl[cur][0];
+}
+
 // Collapse to 4-wide nodes. One CTA, level-synchronous work queue: task = (binary node, output node).
 // Each task opens the interior child with the largest surface area until it has 4 children.
-__global__ void __launch_bounds__(1024) k_bvh_collapse(int n, int root, const int* left, const int* right, const BuildBox* nbox,
+__global__ void __launch_bounds__(1024) k_bvh_collapse(int n, int root, const int* root_dev /* if not null: *root_dev instead of root */,
+                                                       const int* left, const int* right, const BuildBox* nbox,
                                                        const int* sorted, const DTlp* tlps, BVH4Node* out,
                                                        int* n_out, int2* qa, int2* qb) {
   __shared__ int s_count, s_next;
-  if (threadIdx.x == 0) { qa[0] = make_int2(root, 0); s_count = 1; s_next = 0; *n_out = 1; }
+  if (threadIdx.x == 0) { qa[0] = make_int2(root_dev ? *root_dev : root, 0); s_count = 1; s_next = 0; *n_out = 1; }
   __syncthreads();
   int2* cur = qa; int2* nxt = qb;
   while (true) {

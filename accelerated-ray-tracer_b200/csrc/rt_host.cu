@@ -399,6 +399,7 @@ static int upload_scene(rt_scene* s) {
     DBuf<int> left, right; DBuf<BuildBox> nbox; DBuf<int2> qa, qb;
     CU(left.alloc(n)); CU(right.alloc(n)); CU(nbox.alloc(2 * n)); CU(qa.alloc(n)); CU(qb.alloc(n));
     int root = 0;
+    DBuf<int> d_root;  // small scenes: the root stays on the device
     // RT_BVH_BUILDER=lbvh: the plain radix tree over the Morton codes (Karras 2012) instead of PLOC - a different
     // topology over the same leaves, kept for A/B runs and for the test that both return the same hits
     const char* builder = getenv("RT_BVH_BUILDER");
@@ -408,6 +409,11 @@ static int upload_scene(rt_scene* s) {
     CU(cudaMemset(flags.p, 0, n * sizeof(int)));
     k_bvh_karras<<<G, B>>>(k_out.p, n, left.p, right.p, parent.p);
     k_bvh_fit<<<G, B>>>(d_boxes.p, v_out.p, n, left.p, right.p, parent.p, nbox.p, flags.p);
+    } else {
+    if (n <= RT_PLOC_SMALL) {
+      // every scene function of the reference: all PLOC rounds in one launch of one CTA
+      CU(d_root.alloc(1));
+      k_ploc_small<<<1, RT_PLOC_SMALL_THREADS>>>(d_boxes.p, v_out.p, n, nbox.p, left.p, right.p, d_root.p);
     } else {
     // PLOC rounds: nearest neighbour search -> merge -> compaction, until one cluster (the root) is left
     DBuf<int> cl_a, cl_b, nn, next_id, d_m;
@@ -430,7 +436,8 @@ static int upload_scene(rt_scene* s) {
     }
     CU(cudaMemcpy(&root, cl_a.p, sizeof(int), cudaMemcpyDeviceToHost));
     }
-    k_bvh_collapse<<<1, 1024>>>(n, root, left.p, right.p, nbox.p, v_out.p, s->tlp.p, s->nodes.p, d_nout.p, qa.p, qb.p);
+    }
+    k_bvh_collapse<<<1, 1024>>>(n, root, d_root.p, left.p, right.p, nbox.p, v_out.p, s->tlp.p, s->nodes.p, d_nout.p, qa.p, qb.p);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
   }
@@ -480,20 +487,29 @@ extern "C" int rt_build_scene(const rt_scene_desc* desc, rt_scene** out) {
   int dev = desc->device;
   if (dev < 0) { CU(cudaGetDevice(&dev)); }
   CU(cudaSetDevice(dev));
-  rt_scene* s = new rt_scene();
-  s->device = dev;
-  {
-    CudaDevMath dm;
-    std::string err = generate_scene(s->sd, dm, desc->scene_id, desc->nx, desc->ny, desc->grid_half,
-                                     desc->texture_dir ? desc->texture_dir : "");
-    if (!err.empty()) { delete s; return fail("rt_build_scene: " + err); }
-    if (!dm.ok) { delete s; return fail("rt_build_scene: device math service failed"); }
+  rt_scene* s = nullptr;
+  try {
+    s = new rt_scene();
+    s->device = dev;
+    {
+      CudaDevMath dm;
+      std::string err = generate_scene(s->sd, dm, desc->scene_id, desc->nx, desc->ny, desc->grid_half,
+                                       desc->texture_dir ? desc->texture_dir : "");
+      if (!err.empty()) { delete s; return fail("rt_build_scene: " + err); }
+      if (!dm.ok) { delete s; return fail("rt_build_scene: device math service failed"); }
+    }
+    return finish_build(s, dev, out);
+  } catch (const std::exception& e) {
+    delete s;
+    *out = nullptr;
+    return fail(std::string("rt_build_scene: ") + e.what());
   }
-  return finish_build(s, dev, out);
 }
 
 // Build from a caller-made scene description (the flat SD format of rt_scene_desc.h): the generic path behind the
-// scene vocabulary. A scene built this way from rt_scene_export's output renders bit-identically to the original.
+// scene vocabulary. A scene built this way from rt_scene_export's output has the same geometry, materials and camera;
+// the scene function's host parameters (background, gradient, default spp) are not part of an SD and come from
+// rt_render_params (test_scene_from_exported_description_renders_identically passes them).
 extern "C" int rt_build_scene_sd(const void* sd, size_t sd_bytes, const unsigned char* const* image_pixels, int32_t n_images,
                                  int32_t device, rt_scene** out) {
   if (!sd || !out) return fail("rt_build_scene_sd: null argument");
@@ -504,11 +520,18 @@ extern "C" int rt_build_scene_sd(const void* sd, size_t sd_bytes, const unsigned
   int dev = device;
   if (dev < 0) { CU(cudaGetDevice(&dev)); }
   CU(cudaSetDevice(dev));
-  rt_scene* s = new rt_scene();
-  s->device = dev;
-  std::string err = sd_deserialize(sd, sd_bytes, image_pixels, n_images, s->sd);
-  if (!err.empty()) { delete s; return fail("rt_build_scene_sd: " + err); }
-  return finish_build(s, dev, out);
+  rt_scene* s = nullptr;
+  try {  // nothing may throw across the C boundary (bad_alloc on a hostile size, ...)
+    s = new rt_scene();
+    s->device = dev;
+    std::string err = sd_deserialize(sd, sd_bytes, image_pixels, n_images, s->sd);
+    if (!err.empty()) { delete s; return fail("rt_build_scene_sd: " + err); }
+    return finish_build(s, dev, out);
+  } catch (const std::exception& e) {
+    delete s;  // finish_build deletes the scene itself only on the error paths it returns from
+    *out = nullptr;
+    return fail(std::string("rt_build_scene_sd: ") + e.what());
+  }
 }
 
 extern "C" void rt_destroy(rt_scene* s) {
@@ -688,6 +711,8 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     // wave that traced no ray means the pool has run out of work; the job is done when all pools have.
     int batch = 8;
     if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
+    int tail_rays = 16384;  // a pool's wave at or below this many rays (work counter dry) is handed to k_finish; 0: never
+    if (const char* e = getenv("RT_TAIL_RAYS")) tail_rays = std::max(0, atoi(e));
     FILE* wlog = nullptr;  // diagnostics: one line per wave (rays of the wave, k_trace ms, k_shade ms)
     if (p->profile) if (const char* e = getenv("RT_WAVE_LOG")) { wlog = fopen(e, "a"); batch = 1; }
     std::vector<cudaEvent_t> pev;
@@ -744,6 +769,21 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
         for (int q = 0; q < RT_NQ; ++q) last += s->h_counters[k].n_queue[parity ^ 1][q];
         done[k] = last == 0;
         last_all += last;
+        // Tail of the job: once a pool's wave is less than half full the work counter has run dry (finished samples are
+        // no longer replaced), so its waves only shrink from here on: launch grids that fit what is left instead of
+        // grids for the pool's capacity (thousands of blocks that start only to find nothing to do).
+        if (2 * (long long)last < Pp[k].n_slots) {
+            const size_t cap = pool_cap((size_t)last);
+            if (!ref_rng && !wlog && last > 0 && last <= tail_rays) {
+              // few enough paths left: every lane keeps its path to the end in ONE kernel instead of ~40 more waves that
+              // each cost the latency of their slowest ray plus two launches
+              k_finish<<<(int)((cap + 127) / 128), 128, 0, streams[k]>>>(s->dscene, Pp[k], Ap[k], s->counters.p + k, parity);
+              ++launches;
+              done[k] = true;
+            }
+            Gs[k] = (int)std::max<size_t>(1, std::min<size_t>((size_t)Gs[k], (cap + B - 1) / B));
+            Gt[k] = (int)std::max<size_t>(1, std::min<size_t>((size_t)Gt[k], (cap / RT_RANGE + RT_TWARPS - 1) / RT_TWARPS));
+        }
       }
       if (p->profile) {
         for (int w = 0; w < batch; ++w) {
@@ -905,6 +945,13 @@ extern "C" int rt_render_adaptive(rt_scene* s, const rt_render_params* p, const 
     CU(cudaMemcpyAsync(err.data(), d_err.p, n_tiles * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
+    if (const char* e = getenv("RT_ADAPTIVE_LOG")) {  // diagnostics: the error map of every pass, one row of tiles per line
+      if (FILE* f = fopen(e, "a")) {
+        fprintf(f, "pass %d, %d spp:\n", R.passes, done);
+        for (int t = 0; t < n_tiles; ++t) fprintf(f, "%s%.4g%s", active[t] ? "" : "(", err[t], (t + 1) % tiles_x == 0 ? (active[t] ? "\n" : ")\n") : (active[t] ? " " : ") "));
+        fclose(f);
+      }
+    }
     R.err_min = FLT_MAX; R.err_max = 0.f; R.err_spp = done;
     for (int t = 0; t < n_tiles; ++t) if (active[t]) { R.err_min = std::min(R.err_min, err[t]); R.err_max = std::max(R.err_max, err[t]); }
     if (done >= min_spp)

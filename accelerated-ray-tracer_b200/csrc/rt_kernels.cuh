@@ -288,6 +288,78 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
   }
 }
 
+// One event of a path (main.cu:57-83): the hit `hh` of ray r is shaded - miss / background, emission, scatter, throughput.
+// Returns true when the sample has ended; its radiance is then already added to the pixel (reference-RNG mode: the float
+// sum `col += color(...)`, main.cu:124; Philox mode: fixed-point atomics). Otherwise r / thr / bounce hold the next ray.
+// q = shade class of the hit (Q_MISS for a miss). Used by k_shade (one class per warp) and by k_finish (tail of a job).
+template <int MODE, class RNG>
+RT_D bool shade_event(const DScene& S, const RenderParams& P, const PathArrays& A, WaveCounters* C, int q, float2 hh, Ray& r, V3& thr,
+                      int& bounce, int lpix, int sample, RNG& g) {
+  V3 rad = v3(0.f, 0.f, 0.f);
+  bool sample_done;
+  Ray nxt; nxt.o = r.o; nxt.d = r.d; nxt.tm = r.tm;
+  if (q == Q_MISS) {
+    // main.cu:58-68
+    V3 bg = P.background;
+    if (P.gradient) {
+      const float uy = fdiv(r.d.y, vlen(r.d));
+      const float t = fmul(0.5f, fadd(uy, 1.0f));
+      const float omt = fsub(1.0f, t);
+      bg = v3(ffma(t, 0.5f, omt), ffma(t, 0.7f, omt), fadd(t, omt));
+    }
+    rad = v3(ffma(thr.x, bg.x, rad.x), ffma(thr.y, bg.y, rad.y), ffma(thr.z, bg.z, rad.z));
+    sample_done = true;
+  } else {
+    const int packed = __float_as_int(hh.y);
+    const int tlp = packed & (int)RT_TLP_MASK, face = (packed >> 25) & 7;
+    const DTlp T = S.tlp[tlp];
+    const DMat m = S.mats[T.mat];
+    Rec rec;
+    if (ref_type(T.ref) == G_MEDIUM) {  // constant_medium.cuh:58-62
+      rec.t = hh.x;
+      rec.p = vmad(hh.x, r.d, r.o);
+      rec.n = v3(1, 0, 0);
+      rec.u = rec.v = 0.f;
+    } else {
+      geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec, face);
+    }
+    if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
+      const V3 e = material_emitted(S, m, rec);
+      rad = v3(ffma(thr.x, e.x, rad.x), ffma(thr.y, e.y, rad.y), ffma(thr.z, e.z, rad.z));
+    }
+    V3 att;
+    const bool scattered = material_scatter(S, m, r, rec, g, att, nxt);  // main.cu:76
+    if (scattered) {
+      thr = vmul(thr, att);  // main.cu:82
+      ++bounce;
+    }
+    sample_done = !scattered || bounce >= P.max_depth;
+  }
+  if (sample_done) {
+    if constexpr (MODE == RNG_REFERENCE) {
+      // render: col += color(...) (main.cu:124)
+      float4 c = A.col[lpix];
+      c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
+      A.col[lpix] = c;
+    } else {
+      // non-finite samples (and samples too large for the fixed-point sum) are dropped and counted
+      if (fabsf(rad.x) < RT_FIXED_MAX && fabsf(rad.y) < RT_FIXED_MAX && fabsf(rad.z) < RT_FIXED_MAX) {
+        unsigned long long* acc = A.acc64 + 3 * (size_t)lpix;
+        fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
+        if (A.acc64_odd && (sample & 1)) {
+          unsigned long long* ao = A.acc64_odd + 3 * (size_t)lpix;
+          fixed_add(ao + 0, rad.x); fixed_add(ao + 1, rad.y); fixed_add(ao + 2, rad.z);
+        }
+      } else {
+        atomicAdd(&C->nonfinite, 1u);
+      }
+    }
+    return true;
+  }
+  r = nxt;
+  return false;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, RenderParams P, PathArrays A, WaveCounters* C, int parity) {
   const int lane = threadIdx.x & 31;
@@ -336,72 +408,15 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
     lpix = __float_as_int(d.w);
     const SlotInfo si = pixel_info(P, lpix);
     Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
-    V3 thr = v3(thr4.x, thr4.y, thr4.z), rad = v3(0.f, 0.f, 0.f);
+    V3 thr = v3(thr4.x, thr4.y, thr4.z);
     int bounce = __float_as_int(thr4.w) & 255;
     sample = __float_as_int(thr4.w) >> 8;
     rng_load(g, A, P, lpix, si.pix, sample, bounce + 1);
-    bool sample_done;
-    Ray nxt; nxt.o = r.o; nxt.d = r.d; nxt.tm = r.tm;
-    if (q == Q_MISS) {
-      // main.cu:58-68
-      V3 bg = P.background;
-      if (P.gradient) {
-        const float uy = fdiv(r.d.y, vlen(r.d));
-        const float t = fmul(0.5f, fadd(uy, 1.0f));
-        const float omt = fsub(1.0f, t);
-        bg = v3(ffma(t, 0.5f, omt), ffma(t, 0.7f, omt), fadd(t, omt));
-      }
-      rad = v3(ffma(thr.x, bg.x, rad.x), ffma(thr.y, bg.y, rad.y), ffma(thr.z, bg.z, rad.z));
-      sample_done = true;
-    } else {
-      const int packed = __float_as_int(hh.y);
-      const int tlp = packed & (int)RT_TLP_MASK, face = (packed >> 25) & 7;
-      const DTlp T = S.tlp[tlp];
-      const DMat m = S.mats[T.mat];
-      Rec rec;
-      if (ref_type(T.ref) == G_MEDIUM) {  // constant_medium.cuh:58-62
-        rec.t = hh.x;
-        rec.p = vmad(hh.x, r.d, r.o);
-        rec.n = v3(1, 0, 0);
-        rec.u = rec.v = 0.f;
-      } else {
-        geom_hit<true>(S, T.ref, r, P.tmin, FLT_MAX, m.needs_uv != 0, rec, face);
-      }
-      if (q == Q_LIGHT) {  // main.cu:71: radiance += throughput * emitted
-        const V3 e = material_emitted(S, m, rec);
-        rad = v3(ffma(thr.x, e.x, rad.x), ffma(thr.y, e.y, rad.y), ffma(thr.z, e.z, rad.z));
-      }
-      V3 att;
-      const bool scattered = material_scatter(S, m, r, rec, g, att, nxt);  // main.cu:76
-      if (scattered) {
-        thr = vmul(thr, att);  // main.cu:82
-        ++bounce;
-      }
-      sample_done = !scattered || bounce >= P.max_depth;
-    }
-    if (sample_done) {
-      if constexpr (MODE == RNG_REFERENCE) {
-        // render: col += color(...) (main.cu:124)
-        float4 c = A.col[lpix];
-        c.x = fadd(c.x, rad.x); c.y = fadd(c.y, rad.y); c.z = fadd(c.z, rad.z);
-        A.col[lpix] = c;
-      } else {
-        // non-finite samples (and samples too large for the fixed-point sum) are dropped and counted
-        if (fabsf(rad.x) < RT_FIXED_MAX && fabsf(rad.y) < RT_FIXED_MAX && fabsf(rad.z) < RT_FIXED_MAX) {
-          unsigned long long* acc = A.acc64 + 3 * (size_t)lpix;
-          fixed_add(acc + 0, rad.x); fixed_add(acc + 1, rad.y); fixed_add(acc + 2, rad.z);
-          if (A.acc64_odd && (sample & 1)) {
-            unsigned long long* ao = A.acc64_odd + 3 * (size_t)lpix;
-            fixed_add(ao + 0, rad.x); fixed_add(ao + 1, rad.y); fixed_add(ao + 2, rad.z);
-          }
-        } else {
-          atomicAdd(&C->nonfinite, 1u);
-        }
-      }
+    if (shade_event<MODE>(S, P, A, C, q, hh, r, thr, bounce, lpix, sample, g)) {
       need = true;
     } else {
-      A.ray_o[po][gid] = make_float4(nxt.o.x, nxt.o.y, nxt.o.z, nxt.tm);
-      A.ray_d[po][gid] = make_float4(nxt.d.x, nxt.d.y, nxt.d.z, d.w);
+      A.ray_o[po][gid] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
+      A.ray_d[po][gid] = make_float4(r.d.x, r.d.y, r.d.z, d.w);
       A.thr[po][gid] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce | (sample << 8)));
     }
   } else {
@@ -439,6 +454,63 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
     }
     if (live) rng_store(g, A, P, lpix);
   }
+}
+
+// The tail of a job (Philox mode). Once the work counter has run dry the waves shrink bounce after bounce, and a wave of a
+// few thousand rays costs what its slowest ray costs (one warp, ~25 us of dependent loads per closest-hit query) plus two
+// launches - the Book-1 scene at 400x225x10 spent 45 of its 56 waves like that. Here every lane KEEPS its path: trace
+// (one-ray-per-lane traversal) and shade in a loop until the path ends. Same events, same Philox keys (pixel, sample,
+// bounce), fixed-point sums: the image does not change by a bit, whichever wave the hand-over happens at.
+__global__ void __launch_bounds__(128) k_finish(DScene S, RenderParams P, PathArrays A, WaveCounters* C, int parity) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int n = C->order_len;
+  if (gid - lane >= n) return;
+  bool active = false;
+  Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
+  V3 thr = v3(1, 1, 1);
+  int bounce = 0, sample = 0, lpix = 0;
+  if (gid < n) {
+    const float4 d = A.ray_d[parity][gid];
+    if (__float_as_int(d.w) >= 0) {
+      const float4 o = A.ray_o[parity][gid], t4 = A.thr[parity][gid];
+      r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+      thr = v3(t4.x, t4.y, t4.z);
+      bounce = __float_as_int(t4.w) & 255; sample = __float_as_int(t4.w) >> 8;
+      lpix = __float_as_int(d.w);
+      active = true;
+    }
+  }
+  unsigned long long rays = 0;
+  while (__ballot_sync(0xFFFFFFFFu, active)) {
+    const Hit h = closest_hit(S, r, active, P.tmin, FLT_MAX, &C->overflow);
+    if (active) {
+      ++rays;
+      const int q = h.tlp < 0 ? (int)Q_MISS : tlp_class(h.tlp);
+      const float2 hh = make_float2(h.t, __int_as_float(h.tlp < 0 ? RT_HIT_MISS : (tlp_index(h.tlp) | (h.face << 25) | (tlp_class(h.tlp) << 28))));
+      const SlotInfo si = pixel_info(P, lpix);
+      Philox g;
+      rng_load(g, A, P, lpix, si.pix, sample, bounce + 1);
+      if (shade_event<RNG_PHILOX>(S, P, A, C, q, hh, r, thr, bounce, lpix, sample, g)) {
+        // path regeneration, lane by lane (the counter is dry or nearly so by now)
+        const unsigned long long w = atomicAdd(A.next_work, 1ull);
+        if (w < (unsigned long long)P.work_total) {
+          work_to_pixel_sample(P, w, lpix, sample);
+          const SlotInfo s2 = pixel_info(P, lpix);
+          rng_load(g, A, P, lpix, s2.pix, sample, 0);
+          const float u = fdiv(fadd((float)s2.i, g.uniform()), (float)P.nx);
+          const float v = fdiv(fadd((float)s2.j, g.uniform()), (float)P.ny);
+          r = camera_get_ray(S.cam, u, v, g);
+          thr = v3(1.f, 1.f, 1.f); bounce = 0;
+        } else {
+          active = false;
+        }
+      }
+    }
+  }
+  rays = __reduce_add_sync(0xFFFFFFFFu, (unsigned)rays);
+  if (lane == 0 && rays) atomicAdd(&C->rays, rays);
+  if (gid == 0) { C->order_len = 0; for (int q = 0; q < RT_NQ; ++q) { C->n_queue[0][q] = 0; C->n_queue[1][q] = 0; } }
 }
 
 RT_D float apply_gamma(float c, float gamma) {  // main.cu:37-42

@@ -392,6 +392,12 @@ std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* c
     if (t.kind == RT_TEX_CHECKER && (t.even < 0 || t.even >= h.n_tex || t.odd < 0 || t.odd >= h.n_tex)) return "checker child out of range";
     if (t.kind == RT_TEX_UV_OFFSET && (t.even < 0 || t.even >= h.n_tex)) return "uv_offset base out of range";
     if (t.kind == RT_TEX_IMAGE && (t.image < 0 || t.image >= h.n_img)) return "image id out of range";
+    // the octave count is a loop bound on the device (texture.cuh:94-100 -> perlin turb)
+    if (t.kind == RT_TEX_NOODLE && !(t.p[3] >= 0.0f && t.p[3] <= 64.0f)) return "noodle texture: octave count outside 0..64";
+  }
+  for (const auto& d : sd.img) {
+    if (d.width < 0 || d.height < 0 || d.width > 65536 || d.height > 65536 || (d.width > 0 && d.height > 0 && (d.bpp < 3 || d.bpp > 4)))
+      return "image size / channel count out of range";
   }
   for (const auto& m : sd.mat) {
     if (m.kind < RT_MAT_LAMBERTIAN || m.kind > RT_MAT_ISOTROPIC) return "material kind out of range";
@@ -425,7 +431,14 @@ std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* c
       }
     }
   }
-  for (int t : sd.top) if (t < 0 || t >= h.n_obj) return "top-level object out of range";
+  {
+    std::vector<char> seen((size_t)h.n_obj, 0);
+    for (int t : sd.top) {
+      if (t < 0 || t >= h.n_obj) return "top-level object out of range";
+      if (seen[t]) return "top-level list names an object twice";
+      seen[t] = 1;
+    }
+  }
   sd.img_data.resize(h.n_img);
   for (int i = 0; i < h.n_img; ++i) {
     const rt_image_desc& d = sd.img[i];

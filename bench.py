@@ -38,6 +38,12 @@ if PKG not in sys.path:
 METRIC = "Mrays/s (all bounces, device-timed) on Book-2 final scene"
 UNIT = "Mrays/s"
 SCENE_ID, NX, NY = 9, 800, 800
+GRID_HALF = 0
+# --config: the other BASELINE configs as bench lines for profiles/ (the driver's line is always c4)
+CONFIGS = {"c4": (9, 800, 800, 0, 1000, "Book-2 final scene"),
+           "c5-10k": (1, 3840, 2160, 50, 64, "C5 scale-up, 10 004 spheres 3840x2160"),
+           "c5-100k": (1, 3840, 2160, 158, 64, "C5 scale-up, 99 860 spheres 3840x2160"),
+           "c5-1m": (1, 3840, 2160, 500, 64, "C5 scale-up, 1 000 004 spheres 3840x2160")}
 # SURVEY.md §8(d) / BASELINE.md §3: work per ray of the reference algorithm on C4 (fixed normaliser)
 C4_FLOP_PER_RAY = 1685.0
 C4_BYTES_PER_RAY = 2535.0
@@ -258,12 +264,22 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS),
+                    help="workload: c4 (default, BASELINE's headline config) or a C5 scale-up scene (BASELINE configs[4]; "
+                         "sets --spp-per-step 64 unless given; no reference arms: the reference cannot build these scenes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-microbench", action="store_true", help="do not run tools/microbench.cu (measured FP32 / issue / L2 peaks)")
     ap.add_argument("--profile-in-timed", action="store_true",
                     help="record CUDA events around every launch INSIDE the timed region (costs ~7%%); default: the "
                          "per-kernel durations come from one extra, untimed, profiled step of the same workload")
     args = ap.parse_args()
+    global SCENE_ID, NX, NY, GRID_HALF, METRIC
+    if args.config != "c4":
+        SCENE_ID, NX, NY, GRID_HALF, spp_default, what = CONFIGS[args.config]
+        METRIC = "Mrays/s (all bounces, device-timed) on " + what
+        if "--spp-per-step" not in sys.argv:
+            args.spp_per_step = spp_default
+        args.no_cpu_baseline = args.no_reference_cuda = True
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -290,7 +306,8 @@ def main():
             tdist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    sc = pyrt.Scene(SCENE_ID, NX, NY, texture_dir=tex, device=local)
+    sc = pyrt.Scene(SCENE_ID, NX, NY, grid_half=GRID_HALF, texture_dir=tex, device=local)
+    sc_info_n_top, sc_info_nodes, sc_info_bvh_ms = sc.info.n_top, sc.info.n_bvh_nodes, sc.info.bvh_build_ms
     weak = args.scaling == "weak" and world > 1
     S_step = S * world if weak else S          # samples per pixel of one step, all ranks together
     n_steps_all = W + K + 1                     # warm-up + timed + the profiled / parity step
@@ -391,7 +408,7 @@ def main():
         bd = {"build": 0.0, "render_wall": 0.0, "render_device": 0.0, "reduce_readback": 0.0, "destroy": 0.0}
         for i in range(Ke):
             ta = time.perf_counter()
-            s2 = pyrt.Scene(SCENE_ID, NX, NY, texture_dir=tex, device=local)
+            s2 = pyrt.Scene(SCENE_ID, NX, NY, grid_half=GRID_HALF, texture_dir=tex, device=local)
             tb = time.perf_counter()
             st = s2.render(spp=spp_all, rng_mode=0, split_mode=1, rank=(W + i) * world + rank, world=n_steps_all * world)
             tc = time.perf_counter()
@@ -433,6 +450,8 @@ def main():
         trace_s = trace_ms / n_launch / 1e3 if trace_ms > 0 else None
         shade_s = shade_ms / n_launch / 1e3 if shade_ms > 0 else None
         kt, ks, ncu_src = ncu_capture()
+        if args.config != "c4":
+            kt = ks = None  # the committed capture's per-ray figures are C4's (for C5 at 1 M spheres see profiles/*c5*)
         mb = microbench() if not args.no_microbench else None
         trace_rays_per_s = rays_per_launch / trace_s if trace_s else None
         roof = {"bound": "issue", "kernel": "k_trace", "achieved": None, "peak": None, "unit": "Gwarp-inst/s", "frac": None, "traffic": None}
@@ -485,9 +504,12 @@ def main():
             "ms_per_step": round(span_ms / K, 3), "higher_is_better": True, "scaling": "weak" if weak else "strong",
             "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Book-2 final scene (create_world_final + earthmap) 800x800, depth 50, %d spp per step "
-                                   "%s; default 10 steps = the 10000-spp config" %
+            "config": {"workload": ("Book-2 final scene (create_world_final + earthmap) 800x800, depth 50, %d spp per step "
+                                    "%s; default 10 steps = the 10000-spp config" if args.config == "c4" else
+                                    CONFIGS[args.config][5] + " (create_world_bouncing with the grid widened, main.cu:140-141, 160-244), "
+                                    "depth 50, %d spp per step %s") %
                                    (S_step, "(%d per GPU)" % S if weak else "split over the %d GPU(s)" % world),
+                       "name": args.config, "objects": int(sc_info_n_top), "bvh_nodes": int(sc_info_nodes), "bvh_build_ms": round(sc_info_bvh_ms, 3),
                        "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": S_step, "spp_total": S_step * K,
                        "max_depth": 50, "rng": "philox4x32-10", "parallelism": "%s-split x%d, scene replicated" % (args.split if world > 1 else "spp", world),
                        "l2": "inputs larger than L2: %.0f MB of path state (%d slots x 88 B) streamed every wave" %
