@@ -10,7 +10,9 @@
 // --gpus N: the job is split over N devices of this box from ONE process, one host thread and one scene replica per GPU:
 //   --split tile (default)  interleaved scanlines, the shares are assembled on the host; bit-identical to N = 1;
 //   --split spp             every GPU renders all pixels for 1/N of the sample numbers; the linear-radiance buffers are
-//                           summed on GPU 0 over peer memory (rt_accum_reduce) and resolved there (Philox mode only).
+//                           summed on GPU 0 over peer memory (rt_accum_reduce) and resolved there (Philox mode only);
+//   --split dynamic         tile shares (--chunks C of them, default 8 per GPU) handed out at run time to whichever GPU is
+//                           free (rt_render_queue); bit-identical to N = 1.
 // --format: p3 = the reference's text PPM (default), p6 = binary PPM, png; p6/png clamp to 0..255, --clamp does it for p3.
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +29,7 @@ int main(int argc, char** argv) {
   rt_render_params p; memset(&p, 0, sizeof(p));
   d.scene_id = 10;  // what the reference's main() runs
   d.device = -1;
-  int gpus = 1, format = 0, clamp = 0, spp_split = 0;
+  int gpus = 1, format = 0, clamp = 0, spp_split = 0, dynamic = 0, chunks = 0;
   std::string tex = "textures", out;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -41,7 +43,11 @@ int main(int argc, char** argv) {
     else if (a == "--seed") p.seed = strtoull(val(), nullptr, 10);
     else if (a == "--rng") { std::string v = val(); p.rng_mode = (v == "reference" || v == "ref" || v == "xorwow") ? 1 : 0; }
     else if (a == "--gpus") gpus = atoi(val());
-    else if (a == "--split") { std::string v = val(); if (v != "tile" && v != "spp") { fprintf(stderr, "--split tile|spp\n"); return 2; } spp_split = v == "spp"; }
+    else if (a == "--split") {
+      std::string v = val();
+      if (v != "tile" && v != "spp" && v != "dynamic") { fprintf(stderr, "--split tile|spp|dynamic\n"); return 2; }
+      spp_split = v == "spp"; dynamic = v == "dynamic";
+    } else if (a == "--chunks") chunks = atoi(val());
     else if (a == "--textures") tex = val();
     else if (a == "--out") out = val();
     else if (a == "--format") {
@@ -58,6 +64,33 @@ int main(int argc, char** argv) {
   if (gpus < 1) gpus = 1;
   if (gpus == 1) spp_split = 0;
   d.texture_dir = tex.c_str();
+  if (dynamic) {
+    // one scene replica per GPU, then the queue: every replica's host thread pulls tile shares until none is left
+    std::vector<rt_scene*> sc(gpus, nullptr);
+    int rc = 0;
+    for (int r = 0; r < gpus && !rc; ++r) {
+      rt_scene_desc dd = d; dd.device = gpus > 1 ? r : d.device;
+      if (rt_build_scene(&dd, &sc[r])) { fprintf(stderr, "rt_cli: GPU %d: %s\n", r, rt_last_error()); rc = 99; }
+    }
+    rt_scene_info info{}; rt_queue_stats qs{};
+    std::vector<float> img;
+    if (!rc) {
+      rt_scene_info_get(sc[0], &info);
+      img.assign((size_t)info.nx * info.ny * 3, 0.f);
+      if (rt_render_queue(sc.data(), gpus, &p, chunks, img.data(), &qs)) { fprintf(stderr, "rt_cli: %s\n", rt_last_error()); rc = 99; }
+    }
+    for (auto* s : sc) if (s) rt_destroy(s);
+    if (rc) return rc;
+    double ms = 0; for (int r = 0; r < gpus; ++r) if (qs.device_ms[r] > ms) ms = qs.device_ms[r];
+    fprintf(stderr, "Rendering a %dx%d image, scene %d, %d GPU(s) (dynamic queue, %d shares:", info.nx, info.ny, d.scene_id, gpus, qs.n_chunks);
+    for (int r = 0; r < gpus; ++r) fprintf(stderr, " %d", qs.chunks_per_device[r]);
+    fprintf(stderr, "): %.3f ms on the busiest device, %llu rays, %.1f Mrays/s\n", ms, (unsigned long long)qs.rays, ms > 0 ? qs.rays / ms / 1e3 : 0.0);
+    if (rt_write_image(out.empty() ? nullptr : out.c_str(), img.data(), info.nx, info.ny, format, clamp, d.scene_id == 1 ? 1 : 0) < 0) {
+      fprintf(stderr, "rt_cli: %s\n", rt_last_error());
+      return 99;
+    }
+    return 0;
+  }
   std::vector<Share> sh(gpus);
   std::vector<std::thread> th;
   for (int r = 0; r < gpus; ++r)

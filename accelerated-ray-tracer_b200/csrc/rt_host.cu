@@ -909,7 +909,7 @@ extern "C" int rt_render_adaptive(rt_scene* s, const rt_render_params* p, const 
   ad.tile = tile; ad.tiles_x = tiles_x; ad.tiles_y = tiles_y;
   ad.tile_spp.assign(n_tiles, 0);
   std::vector<int> n_even(n_tiles, 0), n_odd(n_tiles, 0), list;
-  std::vector<char> active(n_tiles, 1);
+  std::vector<char> active(n_tiles, 1), below(n_tiles, 0);
   std::vector<float> err(n_tiles, 0.f);
   DBuf<int> d_even, d_odd; DBuf<float> d_err;
   CU(d_even.alloc(std::max(n_tiles, 1))); CU(d_odd.alloc(std::max(n_tiles, 1))); CU(d_err.alloc(std::max(n_tiles, 1)));
@@ -954,8 +954,13 @@ extern "C" int rt_render_adaptive(rt_scene* s, const rt_render_params* p, const 
     }
     R.err_min = FLT_MAX; R.err_max = 0.f; R.err_spp = done;
     for (int t = 0; t < n_tiles; ++t) if (active[t]) { R.err_min = std::min(R.err_min, err[t]); R.err_max = std::max(R.err_max, err[t]); }
-    if (done >= min_spp)
-      for (int t = 0; t < n_tiles; ++t) if (active[t] && err[t] < a->threshold) active[t] = 0;
+    // a tile stops when its estimate has been below the threshold at TWO checks in a row (a single lucky estimate -
+    // the half-buffers agreeing by chance - must not end it), and not before min_spp
+    for (int t = 0; t < n_tiles; ++t) {
+      if (!active[t]) continue;
+      below[t] = err[t] < a->threshold ? below[t] + 1 : 0;
+      if (done >= min_spp && below[t] >= 2) active[t] = 0;
+    }
   }
   ad.on = false;
   // accum = per-pixel MEAN (every tile divides by its own sample count), framebuffer = gamma(mean)

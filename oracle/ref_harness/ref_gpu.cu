@@ -105,9 +105,16 @@ int main(int argc, char** argv) {
   const int nx = a.nx > 0 ? a.nx : sp.nx, ny = a.ny > 0 ? a.ny : sp.ny, ns = a.ns;
   const float gamma = 2.2f;
 
-  // limits as in final_scene / cornell_smoke (main.cu:1132-1133, 1181-1182), enlarged for C5
-  CK(cudaDeviceSetLimit(cudaLimitStackSize, 65536));
-  CK(cudaDeviceSetLimit(cudaLimitMallocHeapSize, (size_t)1024 * 1024 * 1024));
+  // Launch environment of the reference's own scene functions: per-thread stack and device heap exactly as each of them
+  // sets them (main.cu:665-666 and its copies for scenes 1-7: 16 KB / 64 MB; cornell_smoke :1132-1133: 64 KB / 256 MB;
+  // final_scene :1181-1182 and original :1243-1244: 32 KB / 256 MB). Only the C5 scale-up (grid wider than the
+  // reference's 11) gets more heap: its object graph does not fit 64 MB.
+  size_t stack_limit = 16384, heap_limit = (size_t)64 << 20;
+  if (a.scene == 8) { stack_limit = 65536; heap_limit = (size_t)256 << 20; }
+  if (a.scene == 9 || a.scene == 10) { stack_limit = 32768; heap_limit = (size_t)256 << 20; }
+  if (a.scene == 1 && a.grid_half > 11) { stack_limit = 65536; heap_limit = (size_t)1024 << 20; }
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, stack_limit));
+  CK(cudaDeviceSetLimit(cudaLimitMallocHeapSize, heap_limit));
 
   std::string td = a.tex_dir;
   DeviceImage earth{}, ball{};
@@ -117,7 +124,9 @@ int main(int argc, char** argv) {
   if ((a.scene == 3 || a.scene == 9 || a.scene == 10) && !earth.valid()) { fprintf(stderr, "texture missing\n"); return 3; }
 
   const int num_pixels = nx * ny;
-  vec3* fb = dalloc<vec3>(num_pixels);
+  vec3* fb = nullptr;  // managed memory, like every scene function (e.g. main.cu:1192)
+  CK(cudaMallocManaged((void**)&fb, (size_t)num_pixels * sizeof(vec3)));
+  CK(cudaMemset(fb, 0, (size_t)num_pixels * sizeof(vec3)));
   curandState* d_rand_state = dalloc<curandState>(num_pixels);
   curandState* d_rand_state2 = dalloc<curandState>(1);
   rand_init<<<1, 1>>>(d_rand_state2);
@@ -150,6 +159,7 @@ int main(int argc, char** argv) {
   float build_ms = 0; CK(cudaEventElapsedTime(&build_ms, e0, e1));
 
   // ---- export ----
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, 65536));  // harness-only kernels (export, ids) recurse deeper than render()
   RefVptrs* d_vp = dalloc<RefVptrs>(1);
   k_probe<<<1, 1>>>(d_vp);
   CK(cudaDeviceSynchronize());
@@ -208,7 +218,8 @@ int main(int argc, char** argv) {
     fclose(f);
   }
 
-  // ---- stock render, timed like main.cu:699-712 but with events ----
+  // ---- stock render, timed like main.cu:699-712 but with events, under the scene function's own stack limit ----
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, stack_limit));
   float best_ms = 1e30f, sum_ms = 0;
   for (int rep = 0; rep < a.reps; ++rep) {
     CK(cudaEventRecord(e0));

@@ -36,6 +36,18 @@ for sid, nx, ny, spp in [(1, 400, 225, 10), (9, 200, 200, 32)]:
                 msg += "; 8-bit identical to the reference CUDA build: %s" % same8
                 ok &= same8
             print(msg, flush=True)
+    # dynamic tile queue across the ranks (shared counter in the process group's store): bit-identical whoever renders what
+    def share(c, n, sc=sc):
+        st = sc.render(spp=spp, rng_mode=0, rank=c, world=n, split_mode=0)
+        return rdist.fb_tensor(sc).view(st.rows_local, st.nx, 3).clone()
+    full, mine = rdist.render_dynamic(share, 4 * world + 1, ny, nx, device=torch.device("cuda", local))
+    counts = [None] * world
+    torch.distributed.all_gather_object(counts, len(mine))
+    if rank == 0:
+        sc.render(spp=spp, rng_mode=0)
+        same = np.array_equal(sc.framebuffer().view(np.uint32), full.cpu().numpy().view(np.uint32))
+        print("scene %d world %d: dynamic tile queue (%d chunks, per rank %s) bit-identical to 1 GPU: %s" % (sid, world, 4 * world + 1, counts, same), flush=True)
+        ok &= same
     sc.close()
 if rank == 0:
     print("dist_check:", "OK" if ok else "FAILED", flush=True)
