@@ -146,7 +146,10 @@ RT_D V3 texture_value(const DScene& S, int tex, float u, float v, V3 p) {
       }
       case T_FELT: {  // texture.cuh:125-147
         float m = perlin_noise(vscale(t.p[0], p));
-        float phase = ffma(p.x, t.p[2], fmul(2.0f, perlin_turb(vscale(0.5f, p), 2)));
+        // p.x*f_scale + 2*turb: the reference SASS rounds the LEFT product and fuses the right one - FFMA(|turb|, 2,
+        // p.x*f_scale) - unlike every other a*b + c*d site (rt_math.h); fusing the left one was the 1-ulp difference scene
+        // 10 showed in 0.5 % of its pixels in round 1
+        float phase = ffma(perlin_turb(vscale(0.5f, p), 2), 2.0f, fmul(p.x, t.p[2]));
         float fibers = fmul(0.5f, fadd(1.0f, __sinf(phase)));
         float gain = ffma(t.p[3], fsub(fibers, 0.5f), ffma(t.p[1], fsub(m, 0.5f), 1.0f));
         gain = fminf(fmaxf(gain, 0.7f), 1.2f);

@@ -371,7 +371,8 @@ vec3 texture_value(const Scene& S, int tex, float u, float v, vec3 p) {
     }
     case RT_TEX_FELT: {
       const float m = perlin_noise(t.p[0] * p);
-      const float phase = fmaf(p.x, t.p[2], 2.0f * perlin_turb(0.5f * p, 2));
+      // p.x*f_scale + 2*turb: the reference SASS rounds the LEFT product and fuses the right one, FFMA(|turb|, 2, p.x*f_scale)
+      const float phase = fmaf(perlin_turb(0.5f * p, 2), 2.0f, p.x * t.p[2]);
       const float fibers = 0.5f * (1.0f + sinf(phase));
       float gain = fmaf(t.p[3], fibers - 0.5f, fmaf(t.p[1], m - 0.5f, 1.0f));
       gain = fminf(fmaxf(gain, 0.7f), 1.2f);

@@ -66,15 +66,11 @@ def test_reference_rng_mode_matches_reference_cuda_build(pyrt, golden, name, sid
     assert np.array_equal(pos, g["ids_obj"]), "primary-hit object ids"
     assert np.array_equal(t.view(np.uint32), g["ids_t"].view(np.uint32)), "primary-hit t (bit pattern)"
     assert _mat_classes_equal(pyrt, mine_sd, ref_sd, mat, g["ids_mat"]) == 0, "primary-hit material ids"
-    # 3. the image: identical 8-bit output (BASELINE north_star), and bit-identical floats except for a handful of
-    #    1-ulp pixels in the author's felt/noodle textures (scene 10 only)
+    # 3. the image: identical 8-bit output (BASELINE north_star) and bit-identical floats, all ten scenes
     gfb = g["fb"]
     assert np.array_equal(pyrt.to_8bit(fb), pyrt.to_8bit(gfb)), "8-bit image differs from the reference CUDA build"
     nbad = int((fb.view(np.uint32) != gfb.view(np.uint32)).any(axis=2).sum())
-    if sid == 10:
-        assert nbad <= 0.005 * nx * ny and float(np.abs(fb - gfb).max()) <= 2.4e-7
-    else:
-        assert nbad == 0, "%d pixels differ in the float framebuffer" % nbad
+    assert nbad == 0, "%d pixels differ in the float framebuffer" % nbad
     # 4. same ray count as the reference's bounce loop (the golden run's log: tests/golden/ref_gpu/results.jsonl)
     assert st.stack_overflow == 0
     want_rays = _golden_rays(sid, nx, ny, spp)
