@@ -113,7 +113,7 @@ def _psnr(a, b):
 # (golden, scene, our nx, ny, our spp, box-downsample factor of the golden, grid_half)
 CONVERGED = [("c1_400x225_5000", 1, 400, 225, 50000, 1, 0), ("c2_160x160_30000", 7, 160, 160, 400000, 1, 0),
              ("c3_160x160_30000", 8, 160, 160, 400000, 1, 0), ("c4_800x800_1000_ds5", 9, 160, 160, 300000, 5, 0),
-             ("c5_10k_320x180_2000", 1, 320, 180, 40000, 1, 50)]
+             ("c5_10k_320x180_2000", 1, 320, 180, 40000, -4, 50)]
 
 
 @pytest.mark.parametrize("name,sid,nx,ny,spp,ds,gh", CONVERGED, ids=[c[0] for c in CONVERGED])
@@ -133,6 +133,13 @@ def test_converged_image_philox_vs_reference(pyrt, golden, name, sid, nx, ny, sp
         assert st.nonfinite_samples == 0 and st.stack_overflow == 0
     if ds > 1:
         gfb = np.maximum(g["lin_ds"], 0).astype(np.float64) ** (1 / 2.2)
+    elif ds < 0:
+        # The reference golden of this config is only 2000 spp (its render of the 10 004-sphere scene takes 35 s on top of a
+        # 94 s BVH build), which is its own noise floor: 36 dB per pixel. Both images are box-filtered |ds| x |ds| in LINEAR
+        # radiance first (32 000 reference samples per compared pixel), the same footprint integral as the C4 golden.
+        k = -ds
+        pool = lambda im: (np.maximum(im, 0).astype(np.float64) ** 2.2).reshape(ny // k, k, nx // k, k, 3).mean(axis=(1, 3)) ** (1 / 2.2)
+        gfb, fb = pool(g["fb"]), pool(fb)
     else:
         gfb = g["fb"].astype(np.float64)
     fbc, gc = np.clip(fb, 0, 1), np.clip(gfb, 0, 1)
