@@ -726,7 +726,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
       int work_base = 0;  // pool k draws work items [work_base, work_base + n_k) in k_init
       for (int k = 0; k < n_pools; ++k) {
         const int G = (Pp[k].n_slots + B - 1) / B;
-        Gs[k] = (int)((capk[k] + B - 1) / B);
+        Gs[k] = (int)((capk[k] + (size_t)B * RT_SHADE_ITEMS - 1) / ((size_t)B * RT_SHADE_ITEMS));
         Gt[k] = (int)((capk[k] / RT_RANGE + RT_TWARPS - 1) / RT_TWARPS);
         if (ref_rng) k_init<RNG_REFERENCE><<<G, B, 0, streams[k]>>>(s->dscene, Pp[k], Ap[k], work_base);
         else k_init<RNG_PHILOX><<<G, B, 0, streams[k]>>>(s->dscene, Pp[k], Ap[k], work_base);
@@ -781,7 +781,7 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
               ++launches;
               done[k] = true;
             }
-            Gs[k] = (int)std::max<size_t>(1, std::min<size_t>((size_t)Gs[k], (cap + B - 1) / B));
+            Gs[k] = (int)std::max<size_t>(1, std::min<size_t>((size_t)Gs[k], (cap + (size_t)B * RT_SHADE_ITEMS - 1) / ((size_t)B * RT_SHADE_ITEMS)));
             Gt[k] = (int)std::max<size_t>(1, std::min<size_t>((size_t)Gt[k], (cap / RT_RANGE + RT_TWARPS - 1) / RT_TWARPS));
         }
       }

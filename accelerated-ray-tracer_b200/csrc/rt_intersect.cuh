@@ -189,24 +189,33 @@ RT_D bool geom_hit(const SC& S, uint32_t ref, Ray r, float tmin, float tmax, boo
 // ---- constant_medium (constant_medium.cuh:36-76), always entered through the 4-argument overload:
 // the free-flight sample comes from a throw-away XORWOW seeded by a hash of the ray (:69-74), never
 // from the pixel's stream.
-// BH: the boundary's hit routine, (tmin, tmax, float& t) -> bool.
-template <class BH>
-RT_D bool medium_hit_with(const DMedium& m, const Ray& r, float tmin, float tmax, float& t_out, BH boundary_t) {
-  float t1, t2;
-  if (!boundary_t(-FLT_MAX, FLT_MAX, t1)) return false;
-  if (!boundary_t(fadd(t1, 1e-4f), FLT_MAX, t2)) return false;
-  if (t1 < tmin) t1 = tmin;
-  if (t2 > tmax) t2 = tmax;
-  if (t1 >= t2) return false;
-  if (t1 < 0) t1 = 0;
+// BP: the boundary's two queries of lines 43-47, (float& t1, float& t2) -> bool: t1 = first hit in (-FLT_MAX, FLT_MAX),
+// t2 = first hit in (t1 + 1e-4, FLT_MAX).
+// The reference asks the boundary first and draws the free-flight distance after; every exit before the draw returns
+// false and the draw depends on the ray alone, so the order is free. Here the distance comes first, because it allows an
+// EXACT early exit: t2' <= tmax and t1' >= tmin, rounding is monotone, so distance_inside <= (tmax - tmin) * |d| as
+// computed below; a free-flight distance beyond that is rejected by line 66 whatever the boundary says. The thin global
+// mist of the Book-2 final scene (density 1e-4 inside a sphere of radius 5000 that every ray is in) leaves here
+// ~97% of the time once a surface has been found, without its two sphere queries.
+template <class BP>
+RT_D bool medium_hit_with(const DMedium& m, const Ray& r, float tmin, float tmax, float& t_out, BP boundary_pair) {
   const float ray_len = vlen(r.d);
   if (ray_len <= 0.0f || !isfinite(ray_len)) return false;
-  const float distance_inside = fmul(fsub(t2, t1), ray_len);
   uint32_t seed = 1337u ^ f2u(r.o.x) ^ f2u(fmul(r.o.y, 3.1f)) ^ f2u(fmul(r.d.z, 5.7f));
   Xorwow fake;
   fake.init(seed);
   float U = fmaxf(1e-6f, fake.uniform());
   const float hit_distance = fmul(m.neg_inv_density, logf(U));
+#ifndef RT_NO_MEDIUM_EARLY_OUT
+  if (hit_distance > fmul(fsub(tmax, tmin), ray_len)) return false;
+#endif
+  float t1, t2;
+  if (!boundary_pair(t1, t2)) return false;
+  if (t1 < tmin) t1 = tmin;
+  if (t2 > tmax) t2 = tmax;
+  if (t1 >= t2) return false;
+  if (t1 < 0) t1 = 0;
+  const float distance_inside = fmul(fsub(t2, t1), ray_len);
   if (hit_distance > distance_inside) return false;
   t_out = fadd(t1, fdiv(hit_distance, ray_len));
   return true;
@@ -232,10 +241,30 @@ uint2 geom_hit_call(GeomTab G, uint32_t ref, float ox, float oy, float oz, float
 }
 RT_D bool medium_hit(const DScene& S, const DMedium& m, const Ray& r, float tmin, float tmax, float& t_out) {
   const GeomTab G = geom_tab(S);
-  return medium_hit_with(m, r, tmin, tmax, t_out, [&](float a, float b, float& t) {
-    const uint2 h = geom_hit_call(G, m.boundary, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.tm, a, b);
-    t = u2f(h.x);
-    return h.x != 0xFFFFFFFFu;
+  return medium_hit_with(m, r, tmin, tmax, t_out, [&](float& t1, float& t2) {
+    if (ref_type(m.boundary) == G_SPHERE) {
+      // A plain sphere boundary (both media of the Book-2 final scene): the two queries share everything up to the two
+      // roots (sphere.cuh:51-89 evaluated twice on the same ray gives the same roots), so they are computed once.
+      const DSphere s = S.spheres[ref_index(m.boundary)];
+      const V3 cc = vmad(r.tm, v3(s.dx, s.dy, s.dz), v3(s.cx, s.cy, s.cz));
+      const V3 oc = vsub(r.o, cc);
+      const float a = vdot(r.d, r.d), b = vdot(oc, r.d), c = ffma(-s.radius, s.radius, vdot(oc, oc));
+      const float disc = ffma(b, b, -fmul(a, c));
+      if (!(disc > 0.0f)) return false;
+      const float sq = fsqrt(disc);
+      const float r0 = fdiv(fsub(-b, sq), a), r1 = fdiv(fsub(sq, b), a);
+      if (r0 > -FLT_MAX && r0 < FLT_MAX) t1 = r0; else if (r1 > -FLT_MAX && r1 < FLT_MAX) t1 = r1; else return false;
+      const float lo = fadd(t1, 1e-4f);
+      if (r0 > lo && r0 < FLT_MAX) t2 = r0; else if (r1 > lo && r1 < FLT_MAX) t2 = r1; else return false;
+      return true;
+    }
+    const uint2 h1 = geom_hit_call(G, m.boundary, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.tm, -FLT_MAX, FLT_MAX);
+    if (h1.x == 0xFFFFFFFFu) return false;
+    t1 = u2f(h1.x);
+    const uint2 h2 = geom_hit_call(G, m.boundary, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.tm, fadd(t1, 1e-4f), FLT_MAX);
+    if (h2.x == 0xFFFFFFFFu) return false;
+    t2 = u2f(h2.x);
+    return true;
   });
 }
 
@@ -274,10 +303,15 @@ RT_D bool ref_inclusive(const DScene& S, uint32_t ref) {
 #ifndef RT_LEAF_WAIT_MAX
 #define RT_LEAF_WAIT_MAX 6   // ... or when this many lanes have finished their traversal and only wait for their leaves (A/B: 4..8 +5%)
 #endif
+// Media wait for the END of the ray (deferred list, RT_MEDQ entries per lane): a constant_medium is the most expensive
+// leaf by far (free-flight draw + two boundary queries), its result depends on t_max only through the clamp of the exit
+// distance, and with the closest surface already known most of them leave through the exact early exit of
+// medium_hit_with. A lane that collects more than RT_MEDQ - RT_LEAFQ of them makes the warp run a media phase early.
+#define RT_MEDQ (RT_LEAFQ + 2)
 #ifndef RT_NODE_MIN
 #define RT_NODE_MIN 3      // leaf phase starts when fewer lanes than this can still expand a node (A/B on C4: 3 beats 1, 8, 12, 16)
 #endif
-struct Hit { float t; int tlp; int face; };
+struct Hit { float t; int tlp; };  // tlp: -1 (miss) or the PACKED hit word: object index | box face << 25 | shade class << 28
 #ifdef RT_STATS  // diagnostics build only (tools/): per-ray work counters
 __device__ unsigned long long g_stats[8];
 __device__ unsigned long long g_stats2[4];  // per node phase: lanes finished, lanes blocked on a full leaf queue, lanes expanding  // 0 node expansions, 1 sphere tests, 2 geom tests, 3 medium tests, 4 node phases, 5 leaf phases, 6 leaves queued, 7 leaves culled
@@ -293,21 +327,40 @@ RT_D int tlp_index(int word) { return word & (int)RT_TLP_MASK; }
 RT_D int tlp_class(int word) { return (word >> 28) & 7; }
 
 RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int face, Hit& best) {
-  if (t < best.t) { best.t = t; best.tlp = (int)tlp; best.face = face; return; }
+  if (t < best.t) { best.t = t; best.tlp = (int)(tlp | ((uint32_t)face << 25)); return; }
   if (best.tlp < 0) {  // t == the caller's t_max: only an inclusive test accepts that (quad.cuh:64 vs sphere.cuh:63)
-    if (ref_inclusive(S, ref)) { best.t = t; best.tlp = (int)tlp; best.face = face; }
+    if (ref_inclusive(S, ref)) { best.t = t; best.tlp = (int)(tlp | ((uint32_t)face << 25)); }
     return;
   }
   // exact tie (t == best.t; only inclusive tests get here): order semantics of bvh_node::hit
   const int rn = S.tlp[tlp_index((int)tlp)].rank, rb = S.tlp[tlp_index(best.tlp)].rank;
   const bool take = (rn > rb) ? ref_inclusive(S, ref) : !ref_inclusive(S, S.tlp[tlp_index(best.tlp)].ref);
-  if (take) { best.t = t; best.tlp = (int)tlp; best.face = face; }
+  if (take) { best.t = t; best.tlp = (int)(tlp | ((uint32_t)face << 25)); }
 }
 
 // The per-lane arrays live OUTSIDE Trav (a struct with dynamically indexed arrays is kept in local memory as a whole:
 // 84 LDL / 58 STL in k_trace instead of 20 / 15) and are handed to the phases by pointer.
-#define RT_TRAV_ARRAYS(name) uint32_t name##_stack[RT_STACK], name##_lq_ref[RT_LEAFQ], name##_lq_tlp[RT_LEAFQ]; float name##_lq_tn[RT_LEAFQ]
+#define RT_TRAV_ARRAYS(name) uint32_t name##_stack[RT_STACK], name##_lq_ref[RT_LEAFQ], name##_lq_tlp[RT_LEAFQ], name##_mq_tlp[RT_MEDQ]; \
+  float name##_lq_tn[RT_LEAFQ], name##_mq_tn[RT_MEDQ]
 #define RT_TRAV_ARGS(name) name##_stack, name##_lq_ref, name##_lq_tlp, name##_lq_tn
+
+// (p - o) * inv for the four children of one plane vector: two FADD2 + two FMUL2 (add.rn.f32x2 / mul.rn.f32x2)
+RT_D void slab2(const float4 p, float o, float inv, float* out) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long p01, p23, no2, i2, d01, d23;
+  const float no = -o;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(p.x), "f"(p.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(p.z), "f"(p.w));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(no2) : "f"(no));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(i2) : "f"(inv));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(p01), "l"(no2));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(p23), "l"(no2));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(d01), "l"(i2));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(d23), "l"(i2));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(out[0]), "=f"(out[1]) : "l"(d01));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(out[2]), "=f"(out[3]) : "l"(d23));
+#endif
+}
 
 // Per-lane traversal state. The warp-level driver (closest_hit below for one ray per lane; k_trace's loop, which also
 // refills finished lanes with new rays) decides by ballot which phase runs next.
@@ -316,24 +369,27 @@ struct Trav {
   float ix, iy, iz;      // 1.0f / direction, aabb.cuh:48
   float tmin;
   Hit best;
-  int sp, nl;
-  uint32_t cur;
-  bool have;             // holds a node to expand
+  int sp, nl, nm;        // stack entries, pending leaves, deferred media
+  uint32_t cur;          // node to expand next, RT_NODE_EMPTY: none
+  RT_D bool have() const { return cur != RT_NODE_EMPTY; }
 
-  RT_D void reset() { have = false; nl = 0; sp = 0; cur = 0; best.t = FLT_MAX; best.tlp = -1; best.face = 0; }
+  RT_D void reset() { nl = 0; nm = 0; sp = 0; cur = RT_NODE_EMPTY; best.t = FLT_MAX; best.tlp = -1; }
   RT_D void begin(const Ray& ray, float tmin_, float tmax0) {
     r = ray; tmin = tmin_;
-    best.t = tmax0; best.tlp = -1; best.face = 0;
+    best.t = tmax0; best.tlp = -1;
     ix = frcp(r.d.x); iy = frcp(r.d.y); iz = frcp(r.d.z);
-    sp = 0; nl = 0; cur = 0; have = true;
+    sp = 0; nl = 0; nm = 0; cur = 0;
   }
-  RT_D bool can_expand() const { return have && nl <= RT_LEAFQ - 4; }
-  RT_D bool finished() const { return !have && nl == 0; }
+  RT_D bool can_expand() const { return have() && nl <= RT_LEAFQ - 4; }
+  RT_D bool finished() const { return !have() && nl == 0; }
 
   // ---------------- node phase (lanes with can_expand()) ----------------
   RT_D void node_step(const DScene& S, unsigned int* overflow, uint32_t* stack, uint32_t* lq_ref, uint32_t* lq_tlp, float* lq_tn) {
     RT_COUNT(0, 1);
     const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
+#ifdef RT_NODE_PREFETCH
+    const bool big = S.n_nodes > RT_NODE_PREFETCH;  // warp-uniform
+#endif
     // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0. The swap is
     // done by the LOAD: per-ray offsets pick the near / far plane vectors of the node, no per-child selects.
     // float4 index of the NEAR plane vector of each axis inside a node (lox 0, loy 1, loz 2, hix 3, hiy 4, hiz 5)
@@ -348,12 +404,26 @@ struct Trav {
     const float az[4] = {nzp.x, nzp.y, nzp.z, nzp.w}, bz[4] = {fzp.x, fzp.y, fzp.z, fzp.w};
     const uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w}, ct[4] = {tl.x, tl.y, tl.z, tl.w};
     uint32_t key[4];  // interior children that are entered: (entry distance bits, child slot); else 0xFFFFFFFF
+#ifndef RT_NO_PACKED_SLAB
+    // The 48 subtractions and multiplications of the four slab tests as 24 packed f32x2 instructions (sm_100 FADD2 / FMUL2:
+    // two IEEE round-to-nearest operations per issue slot, same bits as the scalar forms; the kernel is issue-bound).
+    float tn_[3][4], tf_[3][4];
+    slab2(nxp, r.o.x, ix, tn_[0]); slab2(fxp, r.o.x, ix, tf_[0]);
+    slab2(nyp, r.o.y, iy, tn_[1]); slab2(fyp, r.o.y, iy, tf_[1]);
+    slab2(nzp, r.o.z, iz, tn_[2]); slab2(fzp, r.o.z, iz, tf_[2]);
+#endif
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       // tmin = t0 > tmin ? t0 : tmin (== fmaxf, NaN keeps tmin); reject when tmax <= tmin.
+#ifndef RT_NO_PACKED_SLAB
+      float lo = fmaxf(tn_[0][c], tmin), hi = fminf(tf_[0][c], best.t);
+      lo = fmaxf(tn_[1][c], lo); hi = fminf(tf_[1][c], hi);
+      lo = fmaxf(tn_[2][c], lo); hi = fminf(tf_[2][c], hi);
+#else
       float lo = fmaxf(fmul(fsub(ax[c], r.o.x), ix), tmin), hi = fminf(fmul(fsub(bx[c], r.o.x), ix), best.t);
       lo = fmaxf(fmul(fsub(ay[c], r.o.y), iy), lo); hi = fminf(fmul(fsub(by[c], r.o.y), iy), hi);
       lo = fmaxf(fmul(fsub(az[c], r.o.z), iz), lo); hi = fminf(fmul(fsub(bz[c], r.o.z), iz), hi);
+#endif
       const bool entered = hi > lo && cr[c] != RT_NODE_EMPTY;
       const bool interior = (cr[c] & RT_NODE_FLAG) != 0;
       // lo >= tmin > 0, so its bit pattern orders like the float; the low two mantissa bits carry the child slot
@@ -371,6 +441,9 @@ struct Trav {
         const uint32_t i = key[k] & 3u;
         const uint32_t c = (i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0]);
         stack[sp++] = c & 0x7FFFFFFFu;
+#ifdef RT_NODE_PREFETCH  // big scenes (nodes in L2 / HBM, not L1): start the deferred child's line on its way now
+        if (big) asm volatile("prefetch.global.L1 [%0];" :: "l"(S.nodes + (c & 0x7FFFFFFFu)));
+#endif
       }
     }
     uint32_t next = RT_NODE_EMPTY;
@@ -378,13 +451,13 @@ struct Trav {
       const uint32_t i = key[0] & 3u;
       next = ((i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0])) & 0x7FFFFFFFu;
     }
-    if (next != RT_NODE_EMPTY) cur = next;
-    else if (sp > 0) cur = stack[--sp];
-    else have = false;
+    cur = next;
+    if (next == RT_NODE_EMPTY && sp > 0) cur = stack[--sp];
   }
 
   // ---------------- leaf phase (the whole warp) ----------------
-  RT_D void leaf_phase(const DScene& S, const uint32_t* lq_ref, const uint32_t* lq_tlp, const float* lq_tn) {
+  // Returns (warp-uniform) whether a media phase has to run before the next leaf phase (a deferred list is nearly full).
+  RT_D bool leaf_phase(const DScene& S, const uint32_t* lq_ref, const uint32_t* lq_tlp, const float* lq_tn, uint32_t* mq_tlp, float* mq_tn) {
     RT_COUNT(6, nl);
     const int nmax = __reduce_max_sync(0xFFFFFFFFu, nl);
     // spheres
@@ -396,11 +469,17 @@ struct Trav {
       }
     }
     // quads, boxes, instances: every lane walks ITS geometry leaves with its own cursor, so that the j-th box test of
-    // all lanes runs in the same iteration (a shared position index left 6 of 32 lanes active in the box code)
+    // all lanes runs in the same iteration (a shared position index left 6 of 32 lanes active in the box code).
+    // The same walk moves the media it passes to the lane's deferred list.
     {
       int kk = 0;
       while (true) {
-        while (kk < nl && ref_type(lq_ref[kk]) == G_SPHERE || kk < nl && ref_type(lq_ref[kk]) == G_MEDIUM) ++kk;
+        while (kk < nl) {
+          const uint32_t ty = ref_type(lq_ref[kk]);
+          if (ty == G_MEDIUM) { mq_tlp[nm] = lq_tlp[kk]; mq_tn[nm] = lq_tn[kk]; ++nm; }
+          else if (ty != G_SPHERE) break;
+          ++kk;
+        }
         const bool has = kk < nl;
         if (__ballot_sync(0xFFFFFFFFu, has) == 0u) break;
         if (has && lq_tn[kk] < best.t) {
@@ -411,18 +490,24 @@ struct Trav {
         ++kk;
       }
     }
-    // media
-    const unsigned mmed = __ballot_sync(0xFFFFFFFFu, [&] { bool any = false; for (int k = 0; k < nl; ++k) any |= ref_type(lq_ref[k]) == G_MEDIUM; return any; }());
-    if (mmed) {
-      for (int k = 0; k < nmax; ++k) {
-        if (k < nl && ref_type(lq_ref[k]) == G_MEDIUM && lq_tn[k] < best.t) {
-          float t;
-          RT_COUNT(3, 1);
-          if (medium_hit(S, S.media[ref_index(lq_ref[k])], r, tmin, best.t, t)) leaf_accept(S, lq_ref[k], lq_tlp[k], t, 0, best);
-        }
+    nl = 0;
+    return __any_sync(0xFFFFFFFFu, nm > RT_MEDQ - RT_LEAFQ);
+  }
+
+  // ---------------- media phase (the whole warp; lanes with active = true evaluate and clear their deferred list) ----------------
+  RT_D void media_phase(const DScene& S, const uint32_t* mq_tlp, const float* mq_tn, bool active) {
+    const int n = active ? nm : 0;
+    const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+    for (int k = 0; k < nmax; ++k) {
+      if (k < n && mq_tn[k] < best.t) {
+        const uint32_t tw = mq_tlp[k];
+        const uint32_t ref = S.tlp[tlp_index((int)tw)].ref;
+        float t;
+        RT_COUNT(3, 1);
+        if (medium_hit(S, S.media[ref_index(ref)], r, tmin, best.t, t)) leaf_accept(S, ref, tw, t, 0, best);
       }
     }
-    nl = 0;
+    if (active) nm = 0;
   }
 
   // Which phase next? Node phase unless too few lanes can expand a node or too many only wait for their leaves.
@@ -431,24 +516,31 @@ struct Trav {
   }
 };
 
-// One ray per lane, no refill (k_aov): the whole warp calls it, lanes without a ray pass active = false.
+// One ray per lane, no refill (k_aov, k_finish): the whole warp calls it, lanes without a ray pass active = false.
 RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
   Trav T;
   RT_TRAV_ARRAYS(m);
   T.reset();
   if (active) T.begin(r, tmin, tmax0);
+  bool flush = false;  // warp-uniform: a deferred media list is nearly full
   while (true) {
     const bool can = T.can_expand();
     const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
     const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, T.nl > 0);
-    if ((mexp | mleaf) == 0u) break;
-    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have && T.nl > 0);  // traversal done, leaves pending
+    const bool done = (mexp | mleaf) == 0u;
+    if (done || flush) {
+      if (__any_sync(0xFFFFFFFFu, T.nm > 0)) T.media_phase(S, m_mq_tlp, m_mq_tn, true);
+      flush = false;
+      if (done) break;
+      continue;
+    }
+    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have() && T.nl > 0);  // traversal done, leaves pending
     if (Trav::pick_node_phase(mexp, mleaf, mwait)) {
       if ((threadIdx.x & 31) == 0) RT_COUNT(4, 1);
       if (can) T.node_step(S, overflow, RT_TRAV_ARGS(m));
     } else {
       if ((threadIdx.x & 31) == 0) RT_COUNT(5, 1);
-      T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn);
+      flush = T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn, m_mq_tlp, m_mq_tn);
     }
   }
   return T.best;

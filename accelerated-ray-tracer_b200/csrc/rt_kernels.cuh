@@ -210,14 +210,22 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
   Trav T;
   RT_TRAV_ARRAYS(m);
   T.reset();
+  bool flush = false;  // warp-uniform: a deferred media list is nearly full
   while (true) {
     const bool fin = T.finished();
     const unsigned mfin = __ballot_sync(0xFFFFFFFFu, fin);
-    if (mfin == 0xFFFFFFFFu || (next < end && __popc(mfin) >= RT_REFILL_MIN)) {
+    const bool refill = mfin == 0xFFFFFFFFu || (next < end && __popc(mfin) >= RT_REFILL_MIN);
+    // media phase: the finished lanes' deferred media, before their hits are stored (or everybody's when a list is nearly full)
+    if (flush || (refill && __any_sync(0xFFFFFFFFu, fin && T.nm > 0))) {
+      T.media_phase(S, m_mq_tlp, m_mq_tn, flush || fin);
+      flush = false;
+      continue;
+    }
+    if (refill) {
       // ---------------- refill: finished lanes store their hit and take the next rays of the range ----------------
       if (fin) {
         if (gid >= 0) {
-          const int packed = T.best.tlp < 0 ? RT_HIT_MISS : (tlp_index(T.best.tlp) | (T.best.face << 25) | (tlp_class(T.best.tlp) << 28));
+          const int packed = T.best.tlp;  // RT_HIT_MISS = -1 or the packed hit word
           hit[gid] = make_float2(T.best.t, __int_as_float(packed));
           gid = -1;
         }
@@ -236,23 +244,30 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       }
       if (next >= end) break;  // everyone finished and the range is drained
       next += __popc(mfin);
+#ifdef RT_PREFETCH  // A/B on C4: no gain (the refill of a 64-ray range happens once)
+      if (next + lane < end) {  // the rays the next refill will take: start their way up from HBM / L2 now
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(ray_d + next + lane));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(ray_o + next + lane));
+      }
+#endif
       continue;
     }
     const bool can = T.can_expand();
     const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
     const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, T.nl > 0);
-    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have && T.nl > 0);  // traversal done, leaves pending
+    const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have() && T.nl > 0);  // traversal done, leaves pending
     if (Trav::pick_node_phase(mexp, mleaf, mwait)) {
       if (lane == 0) RT_COUNT(4, 1);
 #ifdef RT_STATS
-      { const unsigned mblk = __ballot_sync(0xFFFFFFFFu, T.have && !can); if (lane == 0) { atomicAdd(&g_stats2[0], (unsigned long long)__popc(mfin)); atomicAdd(&g_stats2[1], (unsigned long long)__popc(mblk)); atomicAdd(&g_stats2[2], (unsigned long long)__popc(mexp)); } }
+      { const unsigned mblk = __ballot_sync(0xFFFFFFFFu, T.have() && !can); if (lane == 0) { atomicAdd(&g_stats2[0], (unsigned long long)__popc(mfin)); atomicAdd(&g_stats2[1], (unsigned long long)__popc(mblk)); atomicAdd(&g_stats2[2], (unsigned long long)__popc(mexp)); } }
 #endif
       if (can) T.node_step(S, &C->overflow, RT_TRAV_ARGS(m));
     } else {
       if (lane == 0) RT_COUNT(5, 1);
-      T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn);
+      flush = T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn, m_mq_tlp, m_mq_tn);
     }
   }
+#if RT_RANGE <= 64
   // ---- bin the range by material class: ONE atomic per class per warp, positions by ballot ----
   __syncwarp();
   int qk[RT_RANGE_K];
@@ -286,6 +301,43 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       off += __popc(m);
     }
   }
+#else  // long ranges: the same in two rolled passes over the range's hits (just written by this warp: L1 / L2 hits)
+  __syncwarp();
+  int mycnt = 0;  // lane c < Q_COUNT: rays of class c in this range
+#pragma unroll 1
+  for (int g0 = base; g0 < end; g0 += 32) {
+    const int g = g0 + lane;
+    int q = -1;
+    if (g < end) {
+      const int packed = __float_as_int(hit[g].y);
+      if (packed != RT_HIT_HOLE) q = packed < 0 ? (int)Q_MISS : ((packed >> 28) & 7);
+    }
+#pragma unroll
+    for (int c = 0; c < Q_COUNT; ++c) {
+      const int n = __popc(__ballot_sync(0xFFFFFFFFu, q == c));
+      if (lane == c) mycnt += n;
+    }
+  }
+  const int sub = wid & (RT_NSUB - 1);
+  int mybase = 0;  // lane c: next free position of class c's sub-queue for this warp
+  if (lane < Q_COUNT && mycnt > 0) mybase = atomicAdd(&C->n_queue[parity][lane * RT_NSUB + sub], mycnt);
+#pragma unroll 1
+  for (int g0 = base; g0 < end; g0 += 32) {
+    const int g = g0 + lane;
+    int q = -1;
+    if (g < end) {
+      const int packed = __float_as_int(hit[g].y);
+      if (packed != RT_HIT_HOLE) q = packed < 0 ? (int)Q_MISS : ((packed >> 28) & 7);
+    }
+#pragma unroll
+    for (int c = 0; c < Q_COUNT; ++c) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, q == c);
+      const int off = __shfl_sync(0xFFFFFFFFu, mybase, c);
+      if (q == c) queues[(size_t)(c * RT_NSUB + sub) * subcap + off + __popc(m & lt)] = g;
+      if (lane == c) mybase += __popc(m);
+    }
+  }
+#endif
 }
 
 // One event of a path (main.cu:57-83): the hit `hh` of ray r is shaded - miss / background, emission, scatter, throughput.
@@ -360,11 +412,19 @@ RT_D bool shade_event(const DScene& S, const RenderParams& P, const PathArrays& 
   return false;
 }
 
+#ifndef RT_SHADE_ITEMS
+#define RT_SHADE_ITEMS 8   // consecutive chunks of RT_BLOCK queue positions a k_shade block walks (software pipeline, see below)
+#endif
+RT_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// k_shade is bound by the LATENCY of its gathers (queue entry -> path state -> scene records: ncu r02h, 60% of the stall
+// samples on the long scoreboard, 36% of the HBM bandwidth with 19 resident warps per SM), so a block walks RT_SHADE_ITEMS
+// chunks and keeps the next chunk's memory traffic in flight under the current chunk's shading: the next queue entry is
+// loaded into a register one chunk ahead, and as soon as it has arrived the four state records it points to are
+// prefetched into L2 (no destination registers).
 template <int MODE>
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, RenderParams P, PathArrays A, WaveCounters* C, int parity) {
   const int lane = threadIdx.x & 31;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int wstart = gid - lane;
   // warp -> (queue, position): the queues are laid end to end, each padded to a whole warp; one warp scan finds the warp's queue
   const int cnt = lane < RT_NQ ? C->n_queue[parity][lane] : 0;
   const int padded = (cnt + 31) & ~31;
@@ -378,81 +438,106 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
     if (lane < RT_NQ) C->n_queue[parity ^ 1][lane] = 0;  // the next wave's trace fills these
     if (lane == 0) { C->rays += (unsigned long long)rays; C->order_len = total; }  // the next k_trace walks this wave's layout
   }
-  if (wstart >= total) return;
-  const unsigned mq = __ballot_sync(0xFFFFFFFFu, lane < RT_NQ && excl <= wstart);
-  const int qi = 31 - __clz(mq);
-  const int qbase = __shfl_sync(0xFFFFFFFFu, excl, qi), qcount = __shfl_sync(0xFFFFFFFFu, cnt, qi);
-  const int q = qi / RT_NSUB;  // material class: warp-uniform
-  const int pos = gid - qbase;
-  const bool live = pos < qcount;  // else: warp padding between two queues
   const int po = parity ^ 1;
-  bool need = false;     // the sample ended: take the next one
-  typename RngOf<MODE>::type g;
-  int lpix = 0, sample = 0;
-  // Miss and light warps end every sample they hold (main.cu:58-68; lights do not scatter, material.cuh:174-178): their
-  // next work items are reserved NOW, so that the round trip of the atomic overlaps the state loads (taken after the
-  // shading it was 19% of k_shade's stall samples).
-  const bool early = MODE == RNG_PHILOX && (q == Q_MISS || q == Q_LIGHT);
-  unsigned long long w_early = 0;
-  if (early) {
-    const unsigned mlive = __ballot_sync(0xFFFFFFFFu, live);
-    const int leader = __ffs(mlive) - 1;
-    if (lane == leader) w_early = atomicAdd(A.next_work, (unsigned long long)__popc(mlive));
-    w_early = __shfl_sync(0xFFFFFFFFu, w_early, leader) + (unsigned long long)__popc(mlive & ((1u << lane) - 1u));
-  }
-  if (live) {
-    const int idx = A.queues[(size_t)qi * A.subcap + pos];
-    const float4 o = A.ray_o[parity][idx], d = A.ray_d[parity][idx];
-    const float4 thr4 = A.thr[parity][idx];
-    const float2 hh = A.hit[idx];
-    lpix = __float_as_int(d.w);
-    const SlotInfo si = pixel_info(P, lpix);
-    Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
-    V3 thr = v3(thr4.x, thr4.y, thr4.z);
-    int bounce = __float_as_int(thr4.w) & 255;
-    sample = __float_as_int(thr4.w) >> 8;
-    rng_load(g, A, P, lpix, si.pix, sample, bounce + 1);
-    if (shade_event<MODE>(S, P, A, C, q, hh, r, thr, bounce, lpix, sample, g)) {
-      need = true;
-    } else {
-      A.ray_o[po][gid] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
-      A.ray_d[po][gid] = make_float4(r.d.x, r.d.y, r.d.z, d.w);
-      A.thr[po][gid] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce | (sample << 8)));
+  // queue entry of position g (a whole warp asks for its 32 consecutive positions): -1 = padding between two queues
+  auto entry_of = [&](int g, int& qi_out) -> int {
+    const int ws = g - lane;
+    const unsigned mq = __ballot_sync(0xFFFFFFFFu, lane < RT_NQ && excl <= ws);
+    const int qi = 31 - __clz(mq);
+    const int qbase = __shfl_sync(0xFFFFFFFFu, excl, qi), qcount = __shfl_sync(0xFFFFFFFFu, cnt, qi);
+    qi_out = qi;
+    const int pos = g - qbase;
+    return pos < qcount ? A.queues[(size_t)qi * A.subcap + pos] : -1;
+  };
+  int gid = (blockIdx.x * RT_SHADE_ITEMS) * RT_BLOCK + threadIdx.x;
+  if (gid - lane >= total) return;
+  int qi = 0;
+  int idx = entry_of(gid, qi);
+#pragma unroll 1
+  for (int rep = 0; rep < RT_SHADE_ITEMS; ++rep, gid += RT_BLOCK) {
+    if (gid - lane >= total) break;  // warp-uniform
+    const int q = qi / RT_NSUB;  // material class: warp-uniform
+    const bool live = idx >= 0;  // else: warp padding between two queues
+    // next chunk: its queue entry starts its way up now
+    int qi_next = 0, idx_next = -1;
+    const bool more = rep + 1 < RT_SHADE_ITEMS && gid + RT_BLOCK - lane < total;  // warp-uniform
+    if (more) idx_next = entry_of(gid + RT_BLOCK, qi_next);
+    bool need = false;     // the sample ended: take the next one
+    typename RngOf<MODE>::type g;
+    int lpix = 0, sample = 0;
+    // Miss and light warps end every sample they hold (main.cu:58-68; lights do not scatter, material.cuh:174-178): their
+    // next work items are reserved NOW, so that the round trip of the atomic overlaps the state loads (taken after the
+    // shading it was 19% of k_shade's stall samples).
+    const bool early = MODE == RNG_PHILOX && (q == Q_MISS || q == Q_LIGHT);
+    unsigned long long w_early = 0;
+    if (early) {
+      const unsigned mlive = __ballot_sync(0xFFFFFFFFu, live);
+      const int leader = __ffs(mlive) - 1;
+      if (lane == leader) w_early = atomicAdd(A.next_work, (unsigned long long)__popc(mlive));
+      w_early = __shfl_sync(0xFFFFFFFFu, w_early, leader) + (unsigned long long)__popc(mlive & ((1u << lane) - 1u));
     }
-  } else {
-    write_hole(A, po, gid);
-  }
-  // ---- path regeneration (main.cu:119-123): a lane whose sample has ended takes the next one ----
-  if constexpr (MODE == RNG_PHILOX) {
-    const unsigned mneed = __ballot_sync(0xFFFFFFFFu, need);
-    if (mneed) {
-      unsigned long long w = w_early;
-      if (!early) {
-        const int leader = __ffs(mneed) - 1;
-        if (lane == leader) w = atomicAdd(A.next_work, (unsigned long long)__popc(mneed));  // one atomic per warp
-        w = __shfl_sync(0xFFFFFFFFu, w, leader) + (unsigned long long)__popc(mneed & ((1u << lane) - 1u));
+    if (live) {
+      const float4 o = A.ray_o[parity][idx], d = A.ray_d[parity][idx];
+      const float4 thr4 = A.thr[parity][idx];
+      const float2 hh = A.hit[idx];
+      lpix = __float_as_int(d.w);
+      if (idx_next >= 0) {  // the state loads above have arrived, so has the next queue entry: prefetch what it points to
+        prefetch_l2(A.ray_o[parity] + idx_next); prefetch_l2(A.ray_d[parity] + idx_next);
+        prefetch_l2(A.thr[parity] + idx_next); prefetch_l2(A.hit + idx_next);
       }
+      const SlotInfo si = pixel_info(P, lpix);
+      Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
+      V3 thr = v3(thr4.x, thr4.y, thr4.z);
+      int bounce = __float_as_int(thr4.w) & 255;
+      sample = __float_as_int(thr4.w) >> 8;
+      rng_load(g, A, P, lpix, si.pix, sample, bounce + 1);
+      if (shade_event<MODE>(S, P, A, C, q, hh, r, thr, bounce, lpix, sample, g)) {
+        need = true;
+      } else {
+        A.ray_o[po][gid] = make_float4(r.o.x, r.o.y, r.o.z, r.tm);
+        A.ray_d[po][gid] = make_float4(r.d.x, r.d.y, r.d.z, d.w);
+        A.thr[po][gid] = make_float4(thr.x, thr.y, thr.z, __int_as_float(bounce | (sample << 8)));
+      }
+    } else {
+      write_hole(A, po, gid);
+      if (idx_next >= 0) {
+        prefetch_l2(A.ray_o[parity] + idx_next); prefetch_l2(A.ray_d[parity] + idx_next);
+        prefetch_l2(A.thr[parity] + idx_next); prefetch_l2(A.hit + idx_next);
+      }
+    }
+    // ---- path regeneration (main.cu:119-123): a lane whose sample has ended takes the next one ----
+    if constexpr (MODE == RNG_PHILOX) {
+      const unsigned mneed = __ballot_sync(0xFFFFFFFFu, need);
+      if (mneed) {
+        unsigned long long w = w_early;
+        if (!early) {
+          const int leader = __ffs(mneed) - 1;
+          if (lane == leader) w = atomicAdd(A.next_work, (unsigned long long)__popc(mneed));  // one atomic per warp
+          w = __shfl_sync(0xFFFFFFFFu, w, leader) + (unsigned long long)__popc(mneed & ((1u << lane) - 1u));
+        }
+        if (need) {
+          if (w < (unsigned long long)P.work_total) {
+            work_to_pixel_sample(P, w, lpix, sample);
+            const SlotInfo si = pixel_info(P, lpix);
+            rng_load(g, A, P, lpix, si.pix, sample, 0);
+            start_sample(S, P, A, po, gid, si, sample, g);
+          } else {
+            write_hole(A, po, gid);
+          }
+        }
+      }
+    } else {
       if (need) {
-        if (w < (unsigned long long)P.work_total) {
-          work_to_pixel_sample(P, w, lpix, sample);
+        if (sample + 1 < P.sample_base + P.sample_count) {
           const SlotInfo si = pixel_info(P, lpix);
-          rng_load(g, A, P, lpix, si.pix, sample, 0);
-          start_sample(S, P, A, po, gid, si, sample, g);
+          start_sample(S, P, A, po, gid, si, sample + 1, g);  // the pixel's stream carries on
         } else {
           write_hole(A, po, gid);
         }
       }
+      if (live) rng_store(g, A, P, lpix);
     }
-  } else {
-    if (need) {
-      if (sample + 1 < P.sample_base + P.sample_count) {
-        const SlotInfo si = pixel_info(P, lpix);
-        start_sample(S, P, A, po, gid, si, sample + 1, g);  // the pixel's stream carries on
-      } else {
-        write_hole(A, po, gid);
-      }
-    }
-    if (live) rng_store(g, A, P, lpix);
+    idx = idx_next; qi = qi_next;
   }
 }
 
@@ -487,7 +572,7 @@ __global__ void __launch_bounds__(128) k_finish(DScene S, RenderParams P, PathAr
     if (active) {
       ++rays;
       const int q = h.tlp < 0 ? (int)Q_MISS : tlp_class(h.tlp);
-      const float2 hh = make_float2(h.t, __int_as_float(h.tlp < 0 ? RT_HIT_MISS : (tlp_index(h.tlp) | (h.face << 25) | (tlp_class(h.tlp) << 28))));
+      const float2 hh = make_float2(h.t, __int_as_float(h.tlp));
       const SlotInfo si = pixel_info(P, lpix);
       Philox g;
       rng_load(g, A, P, lpix, si.pix, sample, bounce + 1);

@@ -1,0 +1,67 @@
+// packed_bench.cu — issue cost of the sm_100 packed FP32 instructions (FADD2 / FMUL2 / FFMA2) against their scalar forms,
+// alone and interleaved with integer ALU work. Prints warp-instructions per clock per SM.
+#include <cstdio>
+#include <cuda_runtime.h>
+#define ITER 4096
+template <int MODE> __global__ void k(float* out, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  unsigned long long p0, p1, p2, p3, pa, pb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p0) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p1) : "f"(x2), "f"(x3));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(x4), "f"(x5));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p3) : "f"(x6), "f"(x7));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+  int i0 = threadIdx.x, i1 = i0 * 3, i2 = i0 * 5, i3 = i0 * 7;
+#pragma unroll 4
+  for (int it = 0; it < ITER; ++it) {
+    if (MODE == 0) {  // 8 scalar FMUL
+      x0 = __fmul_rn(x0, a); x1 = __fmul_rn(x1, a); x2 = __fmul_rn(x2, a); x3 = __fmul_rn(x3, a);
+      x4 = __fmul_rn(x4, a); x5 = __fmul_rn(x5, a); x6 = __fmul_rn(x6, a); x7 = __fmul_rn(x7, a);
+    } else if (MODE == 1) {  // 4 FMUL2 (same flops)
+      asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p0) : "l"(pa)); asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p1) : "l"(pa));
+      asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p2) : "l"(pa)); asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p3) : "l"(pa));
+    } else if (MODE == 2) {  // 8 scalar FMUL + 8 integer ops
+      x0 = __fmul_rn(x0, a); x1 = __fmul_rn(x1, a); x2 = __fmul_rn(x2, a); x3 = __fmul_rn(x3, a);
+      x4 = __fmul_rn(x4, a); x5 = __fmul_rn(x5, a); x6 = __fmul_rn(x6, a); x7 = __fmul_rn(x7, a);
+      i0 = (i0 ^ it) + i1; i1 = (i1 ^ it) + i2; i2 = (i2 ^ it) + i3; i3 = (i3 ^ it) + i0;
+      i0 = (i0 ^ it) + i1; i1 = (i1 ^ it) + i2; i2 = (i2 ^ it) + i3; i3 = (i3 ^ it) + i0;
+    } else if (MODE == 3) {  // 4 FMUL2 + 8 integer ops
+      asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p0) : "l"(pa)); asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p1) : "l"(pa));
+      asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p2) : "l"(pa)); asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p3) : "l"(pa));
+      i0 = (i0 ^ it) + i1; i1 = (i1 ^ it) + i2; i2 = (i2 ^ it) + i3; i3 = (i3 ^ it) + i0;
+      i0 = (i0 ^ it) + i1; i1 = (i1 ^ it) + i2; i2 = (i2 ^ it) + i3; i3 = (i3 ^ it) + i0;
+    } else if (MODE == 4) {  // 8 integer ops only
+      i0 = (i0 ^ it) + i1; i1 = (i1 ^ it) + i2; i2 = (i2 ^ it) + i3; i3 = (i3 ^ it) + i0;
+      i0 = (i0 ^ it) + i1; i1 = (i1 ^ it) + i2; i2 = (i2 ^ it) + i3; i3 = (i3 ^ it) + i0;
+    } else if (MODE == 5) {  // 4 FFMA2
+      asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p0) : "l"(pa), "l"(pb)); asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p1) : "l"(pa), "l"(pb));
+      asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p2) : "l"(pa), "l"(pb)); asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p3) : "l"(pa), "l"(pb));
+    }
+  }
+  float r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 + (float)(i0 + i1 + i2 + i3);
+  float y0, y1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(p0 ^ p1 ^ p2 ^ p3));
+  if (r + y0 + y1 == 12345.678f) out[0] = r;
+}
+template <int MODE> void run(const char* name, int fl_per_iter, float* d) {
+  cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
+  const int blocks = pr.multiProcessorCount * 8, threads = 256;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k<MODE><<<blocks, threads>>>(d, 1.0000001f, 1e-9f);
+  cudaEventRecord(e0);
+  for (int r = 0; r < 5; ++r) k<MODE><<<blocks, threads>>>(d, 1.0000001f, 1e-9f);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  const double iters = (double)blocks * threads / 32 * ITER;  // warp-iterations
+  const double cyc = ms * 1e-3 * clk * 1e3;
+  printf("{\"mode\": \"%s\", \"ms\": %.4f, \"warp_iterations_per_clk_per_sm\": %.4f, \"clk_per_warp_iteration_per_scheduler\": %.3f}\n", name, ms,
+         iters / cyc / pr.multiProcessorCount, cyc * pr.multiProcessorCount * 4 / iters);
+}
+int main() {
+  float* d; cudaMalloc(&d, 4);
+  run<0>("8 FMUL", 8, d); run<1>("4 FMUL2", 8, d); run<5>("4 FFMA2", 16, d); run<4>("8 int (LOP3+IADD3 x8 = ~16 ALU)", 0, d);
+  run<2>("8 FMUL + 8 int", 8, d); run<3>("4 FMUL2 + 8 int", 8, d);
+  return 0;
+}

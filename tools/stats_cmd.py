@@ -2,7 +2,7 @@
 """tools/stats_cmd.py — per-ray work counters of the traversal (diagnostics library built by tools/build_variant.sh stats -DRT_STATS)."""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["RT_LIB"] = os.path.join(ROOT, "accelerated-ray-tracer_b200", "lib", "variants", "stats.so")
+os.environ["RT_LIB"] = os.environ.get("STATS_LIB") or os.path.join(ROOT, "accelerated-ray-tracer_b200", "lib", "variants", "stats.so")
 sys.path.insert(0, os.path.join(ROOT, "accelerated-ray-tracer_b200")); sys.path.insert(0, ROOT)
 import pyrt
 from bench import texture_dir
