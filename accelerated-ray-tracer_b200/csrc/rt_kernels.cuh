@@ -194,7 +194,12 @@ __global__ void __launch_bounds__(RT_BLOCK) k_init(DScene S, RenderParams P, Pat
 #endif
 #ifndef RT_REFILL_MIN
 #define RT_REFILL_MIN 32    // finished lanes that trigger a refill from the warp's range (A/B on C4: 8 -9%, 16 -6%: refilled lanes
-                            // start at the root while the others are deep in the tree, which desynchronises the warp-wide phases)
+                            // start at the root while the others are deep in the tree, which desynchronises the warp-wide phases).
+                            // Round 2 also tried PERSISTENT warps that refill from chunks of the dense layout taken from a
+                            // counter (or by a fixed stride, next rays prefetched) with two chunk slots in flight: node phases
+                            // per ray 0.375 -> 0.288 (stats build) and 10% fewer warp instructions (ncu r02o), but C4 3.71 /
+                            // 3.48 Grays/s against 4.04: every partial refill runs the refill, media-phase and binning code at
+                            // 8..16 of 32 lanes, and issue utilisation fell from 66% to 55% (long-scoreboard stalls 3.0 -> 4.6).
 #endif
 __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, float tmin, const float4* ray_o, const float4* ray_d,
                                                                     float2* hit, int* queues, int subcap, WaveCounters* C, int parity) {
