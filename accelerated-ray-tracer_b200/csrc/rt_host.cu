@@ -191,6 +191,12 @@ struct rt_scene {
   int device = 0;
   SceneDesc sd;
   std::vector<int> rank;
+  // groups (RT_OBJ_BVH) resolved into instanced members: what the device tables are built from (= sd when there is no group)
+  bool grouped = false;
+  SceneDesc sdx;
+  std::vector<int> rank_x, origin;   // per expanded top-level entry: tie-break rank, index of the entry of sd.top it came from
+  const SceneDesc& flat() const { return grouped ? sdx : sd; }
+  const std::vector<int>& flat_rank() const { return grouped ? rank_x : rank; }
   // flattened scene
   DBuf<DSphere> spheres; DBuf<DQuad> quads; DBuf<DXform> xforms; DBuf<DMedium> media;
   DBuf<DMat> mats; DBuf<DTex> texs; DBuf<DImage> images; DBuf<DTlp> tlp; DBuf<BVH4Node> nodes; DBuf<float4> qplanes;
@@ -228,6 +234,7 @@ struct rt_scene {
 struct Flattener {
   const SceneDesc& sd;
   std::vector<DSphere> spheres; std::vector<DQuad> quads; std::vector<DXform> xforms; std::vector<DMedium> media;
+  bool bad = false;  // met a group (RT_OBJ_BVH) where only geometry can be (e.g. a medium boundary)
   explicit Flattener(const SceneDesc& s) : sd(s) {}
   static DQuad mkquad(const rt_object_desc& o) {
     DQuad q;
@@ -269,6 +276,9 @@ struct Flattener {
       }
       case RT_OBJ_WITH_MATERIAL:  // geometry of the child; the override lives in the top-level entry (upload_scene)
         return flatten(o.child);
+      case RT_OBJ_BVH:  // resolved by expand_groups before the scene gets here; what is left is a group in a place it cannot be
+        bad = true;
+        return make_ref(G_SPHERE, 0);
       case RT_OBJ_MEDIUM: {
         DMedium m; m.boundary = flatten(o.child); m.neg_inv_density = o.neg_inv_density; m.mat = o.mat; m.pad = 0;
         media.push_back(m);
@@ -308,7 +318,7 @@ static int queue_of(const SceneDesc& sd, const rt_material_desc& m) {
 }
 
 static int upload_scene(rt_scene* s) {
-  const SceneDesc& sd = s->sd;
+  const SceneDesc& sd = s->flat();
   Flattener F(sd);
   const int n = (int)sd.top.size();
   std::vector<DTlp> tlp(n);
@@ -325,10 +335,11 @@ static int upload_scene(rt_scene* s) {
     if (mat < 0 || mat >= (int)sd.mat.size()) return fail("upload_scene: top-level object without a material");
     tlp[k].mat = mat;
     tlp[k].queue = queue_of(sd, sd.mat[mat]);
-    tlp[k].rank = s->rank[k];
+    tlp[k].rank = s->flat_rank()[k];
     refs[k] = tlp[k].ref;
     for (int a = 0; a < 3; ++a) { boxes[k].mn[a] = o.box_min[a]; boxes[k].mx[a] = o.box_max[a]; }
   }
+  if (F.bad) return fail("upload_scene: a group (bvh_node) where only geometry can be");
   std::vector<DMat> mats(sd.mat.size());
   for (size_t i = 0; i < sd.mat.size(); ++i) {
     const rt_material_desc& m = sd.mat[i];
@@ -468,6 +479,18 @@ extern "C" const char* rt_last_error(void) { return g_err.c_str(); }
 
 static int finish_build(rt_scene* s, int dev, rt_scene** out) {
   s->rank = reference_leaf_order(s->sd);
+  for (const auto& o : s->sd.obj) s->grouped = s->grouped || o.kind == RT_OBJ_BVH;
+  if (s->grouped) {
+    const std::string err = expand_groups(s->sd, s->sdx, s->origin);
+    if (!err.empty()) { delete s; return fail("rt_build_scene: " + err); }
+    // ties between members of different entries follow the reference order of their entries, then the member order
+    const int n = (int)s->sdx.top.size();
+    std::vector<int> order(n);
+    for (int k = 0; k < n; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return s->rank[s->origin[a]] < s->rank[s->origin[b]]; });
+    s->rank_x.assign(n, 0);
+    for (int pos = 0; pos < n; ++pos) s->rank_x[order[pos]] = pos;
+  }
   if (upload_scene(s)) { delete s; return 1; }
   if (!ctx_acquire(dev, RT_MAX_POOLS * sizeof(WaveCounters), s->ctx)) { delete s; return fail("cudaStreamCreate / cudaMallocHost failed"); }
   s->has_ctx = true;
@@ -531,6 +554,26 @@ extern "C" int rt_build_scene_sd(const void* sd, size_t sd_bytes, const unsigned
     delete s;  // finish_build deletes the scene itself only on the error paths it returns from
     *out = nullptr;
     return fail(std::string("rt_build_scene_sd: ") + e.what());
+  }
+}
+
+extern "C" int rt_sd_flatten(const void* sd, size_t sd_bytes, void* buf, size_t cap, size_t* needed, int32_t* origin, int32_t origin_cap,
+                             int32_t* n_top_out) {
+  if (!sd) return fail("rt_sd_flatten: null argument");
+  try {
+    SceneDesc in, out;
+    std::vector<int> og;
+    std::string err = sd_deserialize(sd, sd_bytes, nullptr, 0, in);
+    if (err.empty()) err = expand_groups(in, out, og);
+    if (!err.empty()) return fail("rt_sd_flatten: " + err);
+    const std::string bin = sd_serialize(out);
+    if (needed) *needed = bin.size();
+    if (buf && cap >= bin.size()) memcpy(buf, bin.data(), bin.size());
+    if (n_top_out) *n_top_out = (int32_t)og.size();
+    if (origin) for (int k = 0; k < (int)og.size() && k < origin_cap; ++k) origin[k] = og[k];
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(std::string("rt_sd_flatten: ") + e.what());
   }
 }
 
@@ -859,7 +902,11 @@ extern "C" int rt_readback(rt_scene* s, float* rgb, int32_t* obj_id, int32_t* ma
   if (rgb) CU(cudaMemcpy(rgb, s->fb.p, n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost));
   if (obj_id || mat_id) {
     if (!s->has_aov) return fail("rt_readback: the last rt_render had aov = 0");
-    if (obj_id) CU(cudaMemcpy(obj_id, s->aov_obj.p, n_pix * sizeof(int), cudaMemcpyDeviceToHost));
+    if (obj_id) {
+      CU(cudaMemcpy(obj_id, s->aov_obj.p, n_pix * sizeof(int), cudaMemcpyDeviceToHost));
+      if (s->grouped)  // a hit on a member of a group reports the top-level entry the group sits in
+        for (size_t i = 0; i < n_pix; ++i) if (obj_id[i] >= 0) obj_id[i] = s->origin[obj_id[i]];
+    }
     if (mat_id) CU(cudaMemcpy(mat_id, s->aov_mat.p, n_pix * sizeof(int), cudaMemcpyDeviceToHost));
   }
   return 0;

@@ -247,6 +247,22 @@ int SceneBuilder::with_material(int obj, int mat) {  // hittable.cuh:166-168: bo
   memcpy(o.box_max, S.obj[obj].box_max, 12);
   return push_obj(o);
 }
+int SceneBuilder::bvh_node(const std::vector<int>& members) {  // bvh.cuh:29-84: box = union of the members' boxes
+  int head = -1;
+  for (int m : members) {
+    rt_object_desc o = obj_clear();
+    o.kind = RT_OBJ_BVH; o.child = m; o.inward = head;
+    V3 mn = get3(S.obj[m].box_min), mx = get3(S.obj[m].box_max);
+    if (head >= 0) {
+      const V3 bmn = get3(S.obj[head].box_min), bmx = get3(S.obj[head].box_max);
+      mn = v3(fminf(mn.x, bmn.x), fminf(mn.y, bmn.y), fminf(mn.z, bmn.z));
+      mx = v3(fmaxf(mx.x, bmx.x), fmaxf(mx.y, bmx.y), fmaxf(mx.z, bmx.z));
+    }
+    set_box(o, mn, mx);
+    head = push_obj(o);
+  }
+  return head;
+}
 int SceneBuilder::constant_medium_tex(int boundary, float density, int tex) {  // constant_medium.cuh:24-25
   rt_object_desc o = obj_clear();
   o.kind = RT_OBJ_MEDIUM; o.child = boundary;
@@ -349,6 +365,95 @@ std::string load_texture_file(const std::string& path, HostImage& out) {
   return path + ": unknown texture format (expected .jpg or .ppm)";
 }
 
+// ---- groups (RT_OBJ_BVH) -> instanced members ----
+namespace {
+bool is_wrapper(int kind) { return kind == RT_OBJ_TRANSLATE || kind == RT_OBJ_ROTATE_Y || kind == RT_OBJ_WITH_MATERIAL; }
+// box of wrapper `w` around a child with box (mn, mx): the wrappers' constructors (aabb.cuh:76-79, hittable.cuh:89-116, 166-168)
+void rebox(rt_object_desc& w, const rt_object_desc& child) {
+  const V3 bmn = get3(child.box_min), bmx = get3(child.box_max);
+  if (w.kind == RT_OBJ_TRANSLATE) {
+    const V3 d = get3(w.offset);
+    set_box(w, vadd(bmn, d), vadd(bmx, d));
+  } else if (w.kind == RT_OBJ_ROTATE_Y) {
+    V3 minp = v3(FLT_MAX, FLT_MAX, FLT_MAX), maxp = v3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        for (int k = 0; k < 2; ++k) {
+          const float x = i ? bmx.x : bmn.x, y = j ? bmx.y : bmn.y, z = k ? bmx.z : bmn.z;
+          const float nx = ffma(w.cos_t, x, fmul(w.sin_t, z)), nz = ffma(w.cos_t, z, -fmul(w.sin_t, x));
+          minp = v3(fminf(minp.x, nx), fminf(minp.y, y), fminf(minp.z, nz));
+          maxp = v3(fmaxf(maxp.x, nx), fmaxf(maxp.y, y), fmaxf(maxp.z, nz));
+        }
+    set_box(w, minp, maxp);
+  } else {
+    set_box(w, bmn, bmx);
+  }
+}
+struct GroupExpander {
+  SceneDesc& out;
+  std::vector<int>& origin;
+  std::vector<int> chain;  // wrappers above the current object, outermost first
+  std::string err;
+  size_t budget = (size_t)1 << 24;  // expanded entries (a group instanced many times multiplies)
+  GroupExpander(SceneDesc& o, std::vector<int>& og) : out(o), origin(og) {}
+  bool ends_in_group(int id) const {
+    while (is_wrapper(out.obj[id].kind)) id = out.obj[id].child;
+    return out.obj[id].kind == RT_OBJ_BVH;
+  }
+  void emit(int id, int k) {
+    if (!err.empty()) return;
+    if (out.top.size() >= budget) { err = "groups expand to more than 2^24 top-level objects"; return; }
+    int cur = id;
+    if (!chain.empty()) {
+      if (out.obj[id].kind == RT_OBJ_MEDIUM) {
+        for (int w : chain) if (out.obj[w].kind != RT_OBJ_WITH_MATERIAL) { err = "a medium cannot be wrapped in an instance"; return; }
+      }
+      int depth = 0;
+      for (int w : chain) depth += out.obj[w].kind != RT_OBJ_WITH_MATERIAL;
+      for (int c = id; is_wrapper(out.obj[c].kind); c = out.obj[c].child) depth += out.obj[c].kind != RT_OBJ_WITH_MATERIAL;
+      if (depth > 4) { err = "more than 4 nested instance wrappers"; return; }
+      for (size_t i = chain.size(); i-- > 0;) {
+        rt_object_desc w = out.obj[chain[i]];
+        w.child = cur;
+        rebox(w, out.obj[cur]);
+        out.obj.push_back(w);
+        cur = (int)out.obj.size() - 1;
+      }
+    }
+    out.top.push_back(cur);
+    origin.push_back(k);
+  }
+  void walk(int id, int k) {
+    if (!err.empty()) return;
+    const rt_object_desc o = out.obj[id];
+    if (is_wrapper(o.kind)) {
+      if (!ends_in_group(id)) { emit(id, k); return; }
+      chain.push_back(id);
+      walk(o.child, k);
+      chain.pop_back();
+    } else if (o.kind == RT_OBJ_BVH) {
+      std::vector<int> members;
+      for (int c = id; c >= 0; c = out.obj[c].inward) members.push_back(out.obj[c].child);
+      for (size_t i = members.size(); i-- > 0;) walk(members[i], k);  // creation order
+    } else {
+      emit(id, k);
+    }
+  }
+};
+}  // namespace
+
+std::string expand_groups(const SceneDesc& sd, SceneDesc& out, std::vector<int>& origin) {
+  out = sd;
+  origin.clear();
+  bool any = false;
+  for (const auto& o : sd.obj) any = any || o.kind == RT_OBJ_BVH;
+  if (!any) { origin.resize(sd.top.size()); for (size_t k = 0; k < sd.top.size(); ++k) origin[k] = (int)k; return ""; }
+  out.top.clear();
+  GroupExpander E(out, origin);
+  for (size_t k = 0; k < sd.top.size() && E.err.empty(); ++k) E.walk(sd.top[k], (int)k);
+  return E.err;
+}
+
 std::string sd_serialize(const SceneDesc& sd) {
   rt_sd_header h;
   memset(&h, 0, sizeof(h));
@@ -406,7 +511,7 @@ std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* c
   }
   for (int i = 0; i < h.n_obj; ++i) {
     const rt_object_desc& o = sd.obj[i];
-    if (o.kind < RT_OBJ_SPHERE || o.kind > RT_OBJ_WITH_MATERIAL) return "object kind out of range";
+    if (o.kind < RT_OBJ_SPHERE || o.kind > RT_OBJ_BVH) return "object kind out of range";
     const bool leaf = o.kind == RT_OBJ_SPHERE || o.kind == RT_OBJ_QUAD;
     if ((leaf || o.kind == RT_OBJ_MEDIUM || o.kind == RT_OBJ_WITH_MATERIAL) && (o.mat < 0 || o.mat >= h.n_mat)) return "object material out of range";
     for (int a = 0; a < 3; ++a)
@@ -415,6 +520,15 @@ std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* c
                                      std::isfinite(o.dc[0]) && std::isfinite(o.dc[1]) && std::isfinite(o.dc[2]))) return "sphere is not finite";
     if (o.kind == RT_OBJ_WITH_MATERIAL) {
       if (o.child < 0 || o.child >= i) return "wrapper child must precede the wrapper";
+    }
+    if (o.kind == RT_OBJ_BVH) {  // a cell of a group: member and next cell were created before it
+      if (o.child < 0 || o.child >= i) return "group member must precede the group";
+      if (o.inward < -1 || o.inward >= i || (o.inward >= 0 && sd.obj[o.inward].kind != RT_OBJ_BVH)) return "group cell chain is broken";
+    }
+    if (o.kind == RT_OBJ_MEDIUM && o.child >= 0 && o.child < i) {
+      int c = o.child;
+      while (sd.obj[c].kind == RT_OBJ_TRANSLATE || sd.obj[c].kind == RT_OBJ_ROTATE_Y || sd.obj[c].kind == RT_OBJ_WITH_MATERIAL) c = sd.obj[c].child;
+      if (sd.obj[c].kind == RT_OBJ_BVH) return "a group (bvh_node) as the boundary of a medium is not supported";
     }
     if (o.kind == RT_OBJ_BOX) {
       if (o.child < 0 || o.child + 6 > h.n_obj) return "box faces out of range";

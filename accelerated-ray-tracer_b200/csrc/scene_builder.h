@@ -88,6 +88,7 @@ class SceneBuilder {
   int translate(int obj, V3 offset);
   int rotate_y(int obj, float angle_degrees);
   int with_material(int obj, int mat);  // hittable.cuh:154-178
+  int bvh_node(const std::vector<int>& members);  // bvh.cuh:29-84 as an object: a group (RT_OBJ_BVH cells); -1 for an empty list
   int constant_medium(int boundary, float density, V3 albedo);
   int constant_medium_tex(int boundary, float density, int tex);
 
@@ -121,6 +122,11 @@ bool load_ppm(const std::string& path, HostImage& out);
 bool load_jpeg(const std::string& path, HostImage& out, std::string& err);  // jpeg_baseline.cpp
 // .jpg / .jpeg (baseline JPEG, decoded like the reference's stbi_load(path, .., 3)) or .ppm (P6). "" or an error message.
 std::string load_texture_file(const std::string& path, HostImage& out);
+// Groups (RT_OBJ_BVH) are resolved before the scene is flattened: every top-level entry whose wrapper chain ends in a group
+// becomes one entry per member under a copy of that chain (boxes recomputed like the wrappers' constructors do), which is
+// what the reference's own final scene does by hand for its sphere cluster (main.cu:545-551). origin[k] = index in sd.top
+// of the entry that expanded entry k came from. Returns "" or an error message; out == sd when the scene has no group.
+std::string expand_groups(const SceneDesc& sd, SceneDesc& out, std::vector<int>& origin);
 std::string sd_serialize(const SceneDesc& sd);  // binary SD file image
 std::string sd_deserialize(const void* buf, size_t bytes, const unsigned char* const* images, int n_images, SceneDesc& sd);  // "" or an error
 

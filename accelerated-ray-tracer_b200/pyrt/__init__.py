@@ -70,7 +70,8 @@ class QueueStatsC(C.Structure):
 
 EXPORTS = ["rt_build_scene", "rt_build_scene_sd", "rt_render", "rt_render_stats_get", "rt_readback", "rt_readback_t", "rt_destroy",
            "rt_last_error", "rt_scene_info_get", "rt_scene_export", "rt_scene_export_host", "rt_accum_device_ptr",
-           "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm", "rt_load_texture", "rt_write_image", "rt_accum_reduce", "rt_render_adaptive", "rt_readback_spp", "rt_render_queue"]
+           "rt_resolve", "rt_fb_device_ptr", "rt_trim_device_cache", "rt_write_ppm", "rt_load_texture", "rt_write_image", "rt_accum_reduce", "rt_render_adaptive", "rt_readback_spp", "rt_render_queue",
+           "rt_sd_flatten"]
 
 _lib = None
 
@@ -104,6 +105,8 @@ def lib():
         L.rt_write_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.rt_write_image.restype = C.c_long
         L.rt_accum_reduce.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
+        L.rt_sd_flatten.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_int32,
+                                    C.POINTER(C.c_int32)]
         L.rt_render_adaptive.argtypes = [C.c_void_p, C.POINTER(RenderParamsC), C.POINTER(AdaptiveParamsC), C.POINTER(AdaptiveStatsC)]
         L.rt_readback_spp.argtypes = [C.c_void_p, C.c_void_p]
         L.rt_render_queue.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(RenderParamsC), C.c_int32, C.c_void_p, C.POINTER(QueueStatsC)]
@@ -202,8 +205,6 @@ class SD:
             return ("felt", self._f(d["color"]), self._f(d["p"][:4]))
         if k == 6:
             return ("uv_offset", self._f(d["p"][:2]), self.tex_key(int(d["even"])))
-        if k == 6:
-            return ("with_material", self.obj_key(int(d["child"]), with_box), self.mat_key(int(d["mat"])), box)
         return ("?", k)
 
     def mat_key(self, m):
@@ -240,10 +241,29 @@ class SD:
         if k == 5:
             return ("medium", self._f(d["neg_inv_density"]), self.obj_key(int(d["child"]), with_box),
                     self.mat_key(int(d["mat"])), box)
+        if k == 6:
+            return ("with_material", self.obj_key(int(d["child"]), with_box), self.mat_key(int(d["mat"])), box)
+        if k == 7:  # a bvh_node used as an object: the members of its cell chain, in creation order
+            members, c = [], i
+            while c >= 0:
+                members.append(int(self.obj[c]["child"])); c = int(self.obj[c]["inward"])
+            return ("bvh", tuple(self.obj_key(m, with_box) for m in reversed(members)), box)
         return ("?", k)
 
     def top_keys(self, with_box=True):
         return [self.obj_key(int(t), with_box) for t in self.top]
+
+
+def sd_flatten(raw):
+    """Host-only (no GPU): validate a scene description and resolve its bvh_node groups into instanced members.
+    Returns (flattened SD, origin array); raises RtError with the validator's reason."""
+    L = lib()
+    need, ntop = C.c_size_t(0), C.c_int32(0)
+    _check(L.rt_sd_flatten(raw, len(raw), None, 0, C.byref(need), None, 0, C.byref(ntop)))
+    buf = (C.c_uint8 * need.value)()
+    origin = np.zeros(ntop.value, dtype=np.int32)
+    _check(L.rt_sd_flatten(raw, len(raw), buf, need.value, C.byref(need), origin.ctypes.data, ntop.value, C.byref(ntop)))
+    return SD(bytes(buf)), origin
 
 
 def export_host(scene_id, nx=0, ny=0, grid_half=0, texture_dir=None):

@@ -106,6 +106,13 @@ int rt_build_scene(const rt_scene_desc* desc, rt_scene** out);
  * parameters (spp, background) are not part of an SD: pass them in rt_render_params (defaults: 10 spp, black). */
 int rt_build_scene_sd(const void* sd, size_t sd_bytes, const unsigned char* const* image_pixels, int32_t n_images,
                       int32_t device, rt_scene** out);
+/* Host-only check of a scene description (no GPU): the validation rt_build_scene_sd applies, then the resolution of
+ * bvh_node groups (RT_OBJ_BVH) into instanced members. Writes the flattened scene (an SD without groups, every member
+ * under a copy of the group's wrapper chain; *needed = its size, copied if cap suffices) and origin[k] = index in the
+ * input's top-level list that flattened top-level entry k came from (up to origin_cap ints; *n_top_out = their number).
+ * Returns 0 or 1 with the reason in rt_last_error(). */
+int rt_sd_flatten(const void* sd, size_t sd_bytes, void* buf, size_t cap, size_t* needed, int32_t* origin, int32_t origin_cap,
+                  int32_t* n_top_out);
 /* render_init + render (main.cu:1207-1209). device_ms / rays may be NULL. */
 int rt_render(rt_scene* s, const rt_render_params* p, double* device_ms, uint64_t* rays);
 int rt_render_stats_get(rt_scene* s, rt_render_stats* out);

@@ -71,8 +71,12 @@ enum rt_obj_kind {
   RT_OBJ_TRANSLATE = 3, /* hittable.cuh:40-69                                      */
   RT_OBJ_ROTATE_Y = 4,  /* hittable.cuh:77-149                                     */
   RT_OBJ_MEDIUM = 5,    /* constant_medium.cuh:17-79; child = boundary, mat = phase function */
-  RT_OBJ_WITH_MATERIAL = 6 /* with_material(obj, mat), hittable.cuh:154-178: child's geometry and box, every hit reports
+  RT_OBJ_WITH_MATERIAL = 6, /* with_material(obj, mat), hittable.cuh:154-178: child's geometry and box, every hit reports
                               `mat` (the OUTERMOST override wins: each wrapper sets rec.mat_ptr after its child's hit) */
+  RT_OBJ_BVH = 7        /* a bvh_node used as an OBJECT (bvh.cuh:29: it is a hittable, so it can sit under translate /
+                           rotate_y / with_material or in d_list): the closest hit over its members. The member list is a
+                           chain of cells: child = one member, inward = id of the next cell of the same group (-1: last);
+                           the group is named by its head cell, whose box is the union of all member boxes. */
 };
 
 typedef struct rt_object_desc {
@@ -80,7 +84,7 @@ typedef struct rt_object_desc {
   int32_t mat;        /* sphere/quad: material; box: material of face 0; medium: isotropic phase material;
                          with_material: the override */
   int32_t child;      /* wrapper: wrapped object; box: id of face 0 (faces are child..child+5) */
-  int32_t inward;     /* quad only */
+  int32_t inward;     /* quad: inward flag; bvh cell: next cell of the group or -1 */
   float c0[3];        /* sphere: center.A */
   float dc[3];        /* sphere: center.B (= c1 - c0; 0 for static) */
   float radius;       /* sphere (may be negative) */

@@ -265,6 +265,26 @@ bool object_hit(const Scene& S, int o, const ray& r, float tmin, float tmax, hit
       if (!object_hit(S, d.child, r, tmin, tmax, rec)) return false;
       rec.mat = d.mat;
       return true;
+    case RT_OBJ_BVH: {
+      // A bvh_node used as an object (bvh.cuh:95-106 entered from a wrapper's hit()): its own box, then the closest hit
+      // over the members, each behind its own box like every leaf of a bvh_node. The nodes between the root and the
+      // leaves hold unions of member boxes and the slab test is monotone in the box, so they reject nothing a member's
+      // box accepts; a plain walk over the member list returns what the tree returns (exact-t ties aside).
+      aabb gb = {V3(d.box_min), V3(d.box_max)};
+      if (!aabb_hit(gb, r, tmin, tmax)) return false;
+      std::vector<int> members;
+      for (int c = o; c >= 0; c = S.obj[c].inward) members.push_back(S.obj[c].child);
+      bool any = false;
+      float closest = tmax;
+      for (size_t i = members.size(); i-- > 0;) {
+        const int m = members[i];
+        aabb mb = {V3(S.obj[m].box_min), V3(S.obj[m].box_max)};
+        if (!aabb_hit(mb, r, tmin, closest)) continue;
+        hit_record tmp;
+        if (object_hit(S, m, r, tmin, closest, tmp)) { any = true; closest = tmp.t; rec = tmp; }
+      }
+      return any;
+    }
   }
   return false;
 }

@@ -112,6 +112,18 @@ class SDBuilder:
         o["box_min"], o["box_max"] = self.obj[child]["box_min"], self.obj[child]["box_max"]
         return self._push(o)
 
+    def bvh(self, members):
+        """bvh_node(list, n) used as an object (bvh.cuh:29): a chain of cells, one per member; returns the head cell."""
+        head = -1
+        for m in members:
+            o = self._obj(7); o["child"] = m; o["inward"] = head
+            lo, hi = self.obj[m]["box_min"].copy(), self.obj[m]["box_max"].copy()
+            if head >= 0:
+                lo, hi = np.minimum(lo, self.obj[head]["box_min"]), np.maximum(hi, self.obj[head]["box_max"])
+            o["box_min"], o["box_max"] = lo, hi
+            head = self._push(o)
+        return head
+
     def add(self, o): self.top.append(o)
 
     def camera(self, lookfrom, lookat, vup, vfov, aperture, focus, t0=0.0, t1=1.0):
@@ -135,7 +147,7 @@ class SDBuilder:
                 b"".join(o.tobytes() for o in self.obj) + np.asarray(self.top, "<i4").tobytes())
 
 
-def random_scene(seed, nx=160, ny=120, n_spheres=60, n_boxes=12, media=True, overrides=False):
+def random_scene(seed, nx=160, ny=120, n_spheres=60, n_boxes=12, media=True, overrides=False, groups=False):
     """A room of random primitives that exercises every hittable / material branch, including the reference's odd
     corners: negative-radius spheres (hollow glass), moving spheres, nested translate(rotate_y(box)), media whose
     boundary is a sphere or an instanced box, objects that touch and overlap."""
@@ -181,6 +193,20 @@ def random_scene(seed, nx=160, ny=120, n_spheres=60, n_boxes=12, media=True, ove
         B.add(B.with_material(B.with_material(B.translate(crate, (0, 0, 7)), mats[4]), mats[6]))
         if media:
             B.add(B.with_material(B.medium(B.sphere((-4, 2, -3), 1.5, mats[5]), 0.8, white), B.isotropic(red)))
+    if groups:
+        # bvh_node used as an object (bvh.cuh:29, RT_OBJ_BVH): a cluster in its own frame under translate(rotate_y(.)) - the
+        # Book-2 final scene's sphere cluster as the book writes it -, the same group instanced twice, a group under a
+        # material override, a group inside a group, members that are instances themselves, and a group straight in d_list
+        cluster = B.bvh([B.sphere(rng.uniform(-1.5, 1.5, 3), 0.25, mats[rng.integers(len(mats))]) for _ in range(40)])
+        B.add(B.translate(B.rotate_y(cluster, 15.0), (-5, 3, -4)))
+        B.add(B.translate(cluster, (6, 5, -6)))
+        pile = B.bvh([B.box((0, 0, 0), (0.6, 0.6, 0.6), mats[1]), B.translate(B.box((0, 0, 0), (0.5, 0.5, 0.5), mats[3]), (0.2, 0.6, 0.1)),
+                      B.translate(B.rotate_y(B.box((0, 0, 0), (0.4, 0.4, 0.4), mats[4]), 40.0), (0.3, 1.1, 0.3))])
+        B.add(B.with_material(B.translate(pile, (2, 0, 6)), mats[2]))
+        B.add(B.translate(B.rotate_y(pile, -25.0), (-2, 0, 7)))
+        nest = B.bvh([B.translate(cluster, (0, 2, 0)), B.sphere((0, 0, 0), 0.9, mats[5]), B.quad((-1, -1, 1.2), (2, 0, 0), (0, 2, 0), mats[0])])
+        B.add(B.translate(nest, (-7, 2, 5)))
+        B.add(B.bvh([B.sphere(rng.uniform((-9, 6, -9), (9, 9, 9)), 0.4, mats[6]) for _ in range(5)]))
     if media:
         B.add(B.medium(B.sphere((3, 3, 0), 2.0, mats[5]), 0.4, B.solid((0.2, 0.4, 0.9))))
         B.add(B.medium(B.translate(B.rotate_y(B.box((0, 0, 0), (2.5, 2.5, 2.5), mats[0]), 25.0), (-6, 0.5, 2)), 0.3, white))

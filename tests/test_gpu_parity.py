@@ -429,8 +429,9 @@ def test_cli_ppm_on_stdout_matches_reference_image(pyrt, golden, built):
     assert bad.returncode == 99 and "unknown scene" in bad.stderr
 
 
-@pytest.mark.parametrize("seed,media,overrides", [(1, False, False), (2, True, False), (3, True, True), (4, False, True)])
-def test_random_scene_matches_oracle(pyrt, built, seed, media, overrides):
+@pytest.mark.parametrize("seed,media,overrides,groups", [(1, False, False, False), (2, True, False, False), (3, True, True, False),
+                                                         (4, False, True, False), (5, False, False, True), (6, True, True, True)])
+def test_random_scene_matches_oracle(pyrt, built, seed, media, overrides, groups):
     """The generic path (rt_build_scene_sd) on random scenes built from the whole vocabulary - moving and negative-radius
     spheres, quads, boxes under translate(rotate_y()), media with sphere and instanced-box boundaries - against the CPU
     oracle on the same bytes: primary-hit object / material bit-exact, t bit-exact (inside a medium: logf, 1e-5),
@@ -440,7 +441,8 @@ def test_random_scene_matches_oracle(pyrt, built, seed, media, overrides):
     import oracle_py
     from sdgen import random_scene
     nx, ny, spp = 160, 120, 4
-    sd = random_scene(seed, nx, ny, media=media, overrides=overrides)   # overrides: with_material wrappers (hittable.cuh:154-178)
+    # overrides: with_material wrappers (hittable.cuh:154-178); groups: bvh_node used as an object (bvh.cuh:29, RT_OBJ_BVH)
+    sd = random_scene(seed, nx, ny, media=media, overrides=overrides, groups=groups)
     o = oracle_py.Oracle(sd)
     o_obj, o_mat, o_t = o.primary_ids(nx, ny)
     o_fb, o_rays = o.render(nx, ny, spp, background=(0.02, 0.03, 0.05))

@@ -150,3 +150,59 @@ def test_oracle_on_random_scenes_is_order_independent(oracle_py, pyrt):
         same = (back == obj) & (t2.view(np.uint32) == t.view(np.uint32))
         assert same.mean() > 0.9995, same.mean()  # exact ties (touching faces of overlapping boxes) may resolve differently
         assert (obj >= 0).mean() > 0.5
+
+
+def test_groups_resolve_to_instanced_members(oracle_py, pyrt):
+    """A bvh_node used as an object (RT_OBJ_BVH, bvh.cuh:29) against its flattening (rt_sd_flatten, host only): the oracle
+    walks the group as the reference's nested bvh_node::hit does (group box, member boxes, closest member hit, in the
+    wrapper's frame); the flattened scene has one top-level entry per member under a copy of the wrapper chain, which is
+    what the library builds its device tables from. Same closest hit, same t bits, same material, and origin[] maps every
+    flattened entry back to the entry of d_list it came from."""
+    from sdgen import random_scene
+    sd = random_scene(11, 128, 96, n_spheres=30, n_boxes=6, media=False, overrides=True, groups=True)
+    flat, origin = pyrt.sd_flatten(sd)
+    parsed = pyrt.SD(sd)
+    assert int(flat.hdr["n_top"]) == len(origin) > int(parsed.hdr["n_top"])
+    assert not (flat.obj["kind"][flat.top] == 7).any() and origin.max() == int(parsed.hdr["n_top"]) - 1
+    assert (np.diff(origin) >= 0).all()  # members stay where their group was in d_list
+    og, mg, tg = oracle_py.Oracle(sd).primary_ids(128, 96)
+    of, mf, tf = oracle_py.Oracle(flat.raw.tobytes()).primary_ids(128, 96)
+    back = np.where(of >= 0, origin[np.maximum(of, 0)], -1)
+    same = (back == og) & (mf == mg) & (tf.view(np.uint32) == tg.view(np.uint32))
+    assert same.mean() > 0.9995, same.mean()  # exact ties between overlapping members may resolve differently
+    in_group = np.isin(og, np.nonzero(np.bincount(origin) > 1)[0])
+    assert in_group.mean() > 0.02  # the groups are actually seen
+
+
+def test_group_descriptions_are_validated(pyrt):
+    """Host-side validation of RT_OBJ_BVH: broken cell chains, a group as a medium boundary and instance chains that get
+    too deep once the group is resolved are refused with a reason."""
+    from sdgen import SDBuilder
+    def base():
+        B = SDBuilder(32, 24)
+        m = B.lambertian(B.solid((0.5, 0.5, 0.5)))
+        B.camera((0, 0, 10), (0, 0, 0), (0, 1, 0), 40.0, 0.0, 10.0)
+        return B, m
+    B, m = base()
+    g = B.bvh([B.sphere((0, 0, 0), 1.0, m), B.sphere((2, 0, 0), 1.0, m)])
+    B.add(B.translate(g, (0, 1, 0)))
+    flat, origin = pyrt.sd_flatten(B.to_bytes())
+    assert list(origin) == [0, 0] and list(flat.obj["kind"][flat.top]) == [3, 3]
+    lo = flat.obj["box_min"][flat.top]
+    assert np.allclose(lo, [[-1, 0, -1], [1, 0, -1]])
+    B, m = base()
+    g = B.bvh([B.sphere((0, 0, 0), 1.0, m)])
+    B.obj[g]["inward"] = g  # a cell that points at itself
+    B.add(g)
+    with pytest.raises(pyrt.RtError, match="group cell chain"):
+        pyrt.sd_flatten(B.to_bytes())
+    B, m = base()
+    g = B.bvh([B.sphere((0, 0, 0), 1.0, m)])
+    B.add(B.medium(g, 0.5, B.solid((1, 1, 1))))
+    with pytest.raises(pyrt.RtError, match="boundary of a medium"):
+        pyrt.sd_flatten(B.to_bytes())
+    B, m = base()
+    inner = B.translate(B.translate(B.translate(B.sphere((0, 0, 0), 1.0, m), (1, 0, 0)), (1, 0, 0)), (1, 0, 0))
+    B.add(B.translate(B.translate(B.bvh([inner]), (0, 1, 0)), (0, 1, 0)))
+    with pytest.raises(pyrt.RtError, match="nested instance wrappers"):
+        pyrt.sd_flatten(B.to_bytes())
