@@ -326,20 +326,39 @@ __device__ unsigned long long g_stats2[4];  // per node phase: lanes finished, l
 RT_D int tlp_index(int word) { return word & (int)RT_TLP_MASK; }
 RT_D int tlp_class(int word) { return (word >> 28) & 7; }
 
-RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t tlp, float t, int face, Hit& best) {
-  if (t < best.t) { best.t = t; best.tlp = (int)(tlp | ((uint32_t)face << 25)); return; }
-  if (best.tlp < 0) {  // t == the caller's t_max: only an inclusive test accepts that (quad.cuh:64 vs sphere.cuh:63)
-    if (ref_inclusive(S, ref)) { best.t = t; best.tlp = (int)(tlp | ((uint32_t)face << 25)); }
+// A pending leaf is remembered as its node and child slot (`entry` = node index << 2 | slot), and so is the best hit
+// while a ray is traced (Best::e = entry | box face << 29); the child's tlp word is fetched from the node ONCE per ray,
+// when the hit is final (Best::resolve), not with every node that is expanded or every hit that is accepted.
+#define RT_ENTRY_MASK 0x1FFFFFFFu
+#define RT_NO_ENTRY 0xFFFFFFFFu
+RT_D uint32_t entry_tlp(const DScene& S, uint32_t entry) { return __ldg(&S.nodes[entry >> 2].tlp[entry & 3u]); }
+RT_D uint32_t entry_ref(const DScene& S, uint32_t entry) { return __ldg(&S.nodes[entry >> 2].child[entry & 3u]); }
+struct Best {
+  float t; uint32_t e;
+  RT_D bool none() const { return e == RT_NO_ENTRY; }
+  RT_D Hit resolve(const DScene& S) const {
+    Hit h; h.t = t;
+    h.tlp = none() ? -1 : (int)(entry_tlp(S, e & RT_ENTRY_MASK) | ((e >> 29) << 25));
+    return h;
+  }
+};
+RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t entry, float t, int face, Best& best) {
+  const uint32_t e = entry | ((uint32_t)face << 29);
+  if (t < best.t) { best.t = t; best.e = e; return; }
+  if (best.none()) {  // t == the caller's t_max: only an inclusive test accepts that (quad.cuh:64 vs sphere.cuh:63)
+    if (ref_inclusive(S, ref)) { best.t = t; best.e = e; }
     return;
   }
   // exact tie (t == best.t; only inclusive tests get here): order semantics of bvh_node::hit
-  const int rn = S.tlp[tlp_index((int)tlp)].rank, rb = S.tlp[tlp_index(best.tlp)].rank;
-  const bool take = (rn > rb) ? ref_inclusive(S, ref) : !ref_inclusive(S, S.tlp[tlp_index(best.tlp)].ref);
-  if (take) { best.t = t; best.tlp = (int)(tlp | ((uint32_t)face << 25)); }
+  const uint32_t tn = entry_tlp(S, entry), tb = entry_tlp(S, best.e & RT_ENTRY_MASK);
+  const int rn = S.tlp[tlp_index((int)tn)].rank, rb = S.tlp[tlp_index((int)tb)].rank;
+  const bool take = (rn > rb) ? ref_inclusive(S, ref) : !ref_inclusive(S, S.tlp[tlp_index((int)tb)].ref);
+  if (take) { best.t = t; best.e = e; }
 }
 
 // The per-lane arrays live OUTSIDE Trav (a struct with dynamically indexed arrays is kept in local memory as a whole:
 // 84 LDL / 58 STL in k_trace instead of 20 / 15) and are handed to the phases by pointer.
+// (lq_tlp / mq_tlp hold `entry` words: node index << 2 | child slot)
 #define RT_TRAV_ARRAYS(name) uint32_t name##_stack[RT_STACK], name##_lq_ref[RT_LEAFQ], name##_lq_tlp[RT_LEAFQ], name##_mq_tlp[RT_MEDQ]; \
   float name##_lq_tn[RT_LEAFQ], name##_mq_tn[RT_MEDQ]
 #define RT_TRAV_ARGS(name) name##_stack, name##_lq_ref, name##_lq_tlp, name##_lq_tn
@@ -368,15 +387,15 @@ struct Trav {
   Ray r;
   float ix, iy, iz;      // 1.0f / direction, aabb.cuh:48
   float tmin;
-  Hit best;
+  Best best;
   int sp, nl, nm;        // stack entries, pending leaves, deferred media
   uint32_t cur;          // node to expand next, RT_NODE_EMPTY: none
   RT_D bool have() const { return cur != RT_NODE_EMPTY; }
 
-  RT_D void reset() { nl = 0; nm = 0; sp = 0; cur = RT_NODE_EMPTY; best.t = FLT_MAX; best.tlp = -1; }
+  RT_D void reset() { nl = 0; nm = 0; sp = 0; cur = RT_NODE_EMPTY; best.t = FLT_MAX; best.e = RT_NO_ENTRY; }
   RT_D void begin(const Ray& ray, float tmin_, float tmax0) {
     r = ray; tmin = tmin_;
-    best.t = tmax0; best.tlp = -1;
+    best.t = tmax0; best.e = RT_NO_ENTRY;
     ix = frcp(r.d.x); iy = frcp(r.d.y); iz = frcp(r.d.z);
     sp = 0; nl = 0; nm = 0; cur = 0;
   }
@@ -398,11 +417,10 @@ struct Trav {
     const float4 nyp = __ldg(np + ony), fyp = __ldg(np + (5 - ony));
     const float4 nzp = __ldg(np + onz), fzp = __ldg(np + (7 - onz));
     const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
-    const uint4 tl = __ldg(reinterpret_cast<const uint4*>(np + 7));
     const float ax[4] = {nxp.x, nxp.y, nxp.z, nxp.w}, bx[4] = {fxp.x, fxp.y, fxp.z, fxp.w};
     const float ay[4] = {nyp.x, nyp.y, nyp.z, nyp.w}, by[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
     const float az[4] = {nzp.x, nzp.y, nzp.z, nzp.w}, bz[4] = {fzp.x, fzp.y, fzp.z, fzp.w};
-    const uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w}, ct[4] = {tl.x, tl.y, tl.z, tl.w};
+    const uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w};
     uint32_t key[4];  // interior children that are entered: (entry distance bits, child slot); else 0xFFFFFFFF
 #ifndef RT_NO_PACKED_SLAB
     // The 48 subtractions and multiplications of the four slab tests as 24 packed f32x2 instructions (sm_100 FADD2 / FMUL2:
@@ -428,7 +446,7 @@ struct Trav {
       const bool interior = (cr[c] & RT_NODE_FLAG) != 0;
       // lo >= tmin > 0, so its bit pattern orders like the float; the low two mantissa bits carry the child slot
       key[c] = (entered && interior) ? ((__float_as_uint(lo) & ~3u) | (uint32_t)c) : 0xFFFFFFFFu;
-      if (entered && !interior) { lq_ref[nl] = cr[c]; lq_tlp[nl] = ct[c]; lq_tn[nl] = lo; ++nl; }  // leaves need no order
+      if (entered && !interior) { lq_ref[nl] = cr[c]; lq_tlp[nl] = (cur << 2) | (uint32_t)c; lq_tn[nl] = lo; ++nl; }  // leaves need no order
     }
     // interior children: nearest is the next node, the others are stacked far-to-near (5-comparator network on keys)
 #define RT_KSWAP(a, b) do { const uint32_t lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; } while (0)
@@ -500,11 +518,11 @@ struct Trav {
     const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
     for (int k = 0; k < nmax; ++k) {
       if (k < n && mq_tn[k] < best.t) {
-        const uint32_t tw = mq_tlp[k];
-        const uint32_t ref = S.tlp[tlp_index((int)tw)].ref;
+        const uint32_t entry = mq_tlp[k];
+        const uint32_t ref = entry_ref(S, entry);
         float t;
         RT_COUNT(3, 1);
-        if (medium_hit(S, S.media[ref_index(ref)], r, tmin, best.t, t)) leaf_accept(S, ref, tw, t, 0, best);
+        if (medium_hit(S, S.media[ref_index(ref)], r, tmin, best.t, t)) leaf_accept(S, ref, entry, t, 0, best);
       }
     }
     if (active) nm = 0;
@@ -543,7 +561,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
       flush = T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn, m_mq_tlp, m_mq_tn);
     }
   }
-  return T.best;
+  return T.best.resolve(S);
 }
 
 }  // namespace rt

@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       // ---------------- refill: finished lanes store their hit and take the next rays of the range ----------------
       if (fin) {
         if (gid >= 0) {
-          const int packed = T.best.tlp;  // RT_HIT_MISS = -1 or the packed hit word
-          hit[gid] = make_float2(T.best.t, __int_as_float(packed));
+          const Hit h = T.best.resolve(S);  // RT_HIT_MISS = -1 or the packed hit word
+          hit[gid] = make_float2(h.t, __int_as_float(h.tlp));
           gid = -1;
         }
         const int g = next + __popc(mfin & lt);
