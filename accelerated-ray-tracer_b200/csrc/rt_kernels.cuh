@@ -456,6 +456,28 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
   };
   int gid = (blockIdx.x * RT_SHADE_ITEMS) * RT_BLOCK + threadIdx.x;
   if (gid - lane >= total) return;
+  // Miss and light warps end every sample they hold (main.cu:58-68; lights do not scatter, material.cuh:174-178), so how many
+  // new work items this warp will need for them is known from the queue layout alone. They are reserved NOW, for all the
+  // warp's chunks with ONE atomic on the work counter: its round trip overlaps the first state loads, and the counter - one
+  // address for the whole GPU - sees 1/RT_SHADE_ITEMS of the atomics (one per warp and chunk was 17% of k_shade's stall
+  // samples, ncu r02h).
+  unsigned long long w_early = 0;  // this warp's reservation: items w_early .. are handed to its miss / light lanes in order
+#ifndef RT_NO_EARLY_BLOCK
+  if constexpr (MODE == RNG_PHILOX) {
+    int n_early = 0;
+#pragma unroll 1
+    for (int rep = 0, ws = gid - lane; rep < RT_SHADE_ITEMS && ws < total; ++rep, ws += RT_BLOCK) {
+      const unsigned mq = __ballot_sync(0xFFFFFFFFu, lane < RT_NQ && excl <= ws);
+      const int qq = 31 - __clz(mq), cls = qq / RT_NSUB;
+      const int qbase = __shfl_sync(0xFFFFFFFFu, excl, qq), qcount = __shfl_sync(0xFFFFFFFFu, cnt, qq);
+      if (cls == Q_MISS || cls == Q_LIGHT) n_early += max(0, min(32, qcount - (ws - qbase)));
+    }
+    if (n_early > 0) {
+      if (lane == 0) w_early = atomicAdd(A.next_work, (unsigned long long)n_early);
+      w_early = __shfl_sync(0xFFFFFFFFu, w_early, 0);
+    }
+  }
+#endif
   int qi = 0;
   int idx = entry_of(gid, qi);
 #pragma unroll 1
@@ -470,16 +492,19 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
     bool need = false;     // the sample ended: take the next one
     typename RngOf<MODE>::type g;
     int lpix = 0, sample = 0;
-    // Miss and light warps end every sample they hold (main.cu:58-68; lights do not scatter, material.cuh:174-178): their
-    // next work items are reserved NOW, so that the round trip of the atomic overlaps the state loads (taken after the
-    // shading it was 19% of k_shade's stall samples).
-    const bool early = MODE == RNG_PHILOX && (q == Q_MISS || q == Q_LIGHT);
-    unsigned long long w_early = 0;
+    const bool early = MODE == RNG_PHILOX && (q == Q_MISS || q == Q_LIGHT);  // this chunk's lanes take their items from the reservation
+    unsigned long long w_mine = 0;
     if (early) {
       const unsigned mlive = __ballot_sync(0xFFFFFFFFu, live);
+#ifdef RT_NO_EARLY_BLOCK
       const int leader = __ffs(mlive) - 1;
       if (lane == leader) w_early = atomicAdd(A.next_work, (unsigned long long)__popc(mlive));
-      w_early = __shfl_sync(0xFFFFFFFFu, w_early, leader) + (unsigned long long)__popc(mlive & ((1u << lane) - 1u));
+      w_early = __shfl_sync(0xFFFFFFFFu, w_early, leader);
+      w_mine = w_early + (unsigned long long)__popc(mlive & ((1u << lane) - 1u));
+#else
+      w_mine = w_early + (unsigned long long)__popc(mlive & ((1u << lane) - 1u));
+      w_early += (unsigned long long)__popc(mlive);
+#endif
     }
     if (live) {
       const float4 o = A.ray_o[parity][idx], d = A.ray_d[parity][idx];
@@ -514,7 +539,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
     if constexpr (MODE == RNG_PHILOX) {
       const unsigned mneed = __ballot_sync(0xFFFFFFFFu, need);
       if (mneed) {
-        unsigned long long w = w_early;
+        unsigned long long w = w_mine;
         if (!early) {
           const int leader = __ffs(mneed) - 1;
           if (lane == leader) w = atomicAdd(A.next_work, (unsigned long long)__popc(mneed));  // one atomic per warp
