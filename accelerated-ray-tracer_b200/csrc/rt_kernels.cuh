@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
     }
     if (n_early > 0) {
       if (lane == 0) w_early = atomicAdd(A.next_work, (unsigned long long)n_early);
-      w_early = __shfl_sync(0xFFFFFFFFu, w_early, 0);
+      w_early = __shfl_sync(0xFFFFFFFFu, w_early, 0);  // (one atomic per BLOCK through shared memory: no further gain, A/B r02u)
     }
   }
 #endif
