@@ -678,7 +678,9 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
   if (ref_rng) {
     P.n_slots = (int)n_pix;  // a slot is a pixel: one sequential XORWOW stream each
   } else {
-    long long target = p->slots > 0 ? p->slots : 8 * 1024 * 1024;  // sweep on C4 (4 pools): 2 Mi 3737, 8 Mi 3825 Mrays/s: longer kernels, smaller tails
+    // paths in flight. Sweep on C4, 1000 spp (4 pools): 4 Mi 4080, 8 Mi 4280, 16 Mi 4388, 32 Mi 4486, 64 Mi 4537 Mrays/s (longer
+    // kernels, fewer kernel tails); the same order at 30 and 125 spp. 32 Mi paths = 4.2 GB of path state and queues.
+    long long target = p->slots > 0 ? p->slots : 32 * 1024 * 1024;
     if (p->slots <= 0) if (const char* e = getenv("RT_SLOTS")) target = atoll(e);
     target = (target + 127) / 128 * 128;
     P.n_slots = (int)std::max<long long>(0, std::min<long long>(target, P.work_total));

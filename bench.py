@@ -512,8 +512,8 @@ def main():
                        "name": args.config, "objects": int(sc_info_n_top), "bvh_nodes": int(sc_info_nodes), "bvh_build_ms": round(sc_info_bvh_ms, 3),
                        "scene_id": SCENE_ID, "nx": NX, "ny": NY, "spp_per_step": S_step, "spp_total": S_step * K,
                        "max_depth": 50, "rng": "philox4x32-10", "parallelism": "%s-split x%d, scene replicated" % (args.split if world > 1 else "spp", world),
-                       "l2": "inputs larger than L2: %.0f MB of path state (%d slots x 88 B) streamed every wave" %
-                             (st.n_slots * 88 / 1e6, st.n_slots)},
+                       "l2": "inputs larger than L2: %.0f MB of path state (%d paths in flight x 104 B: two ping-pong sets of 48 B + an 8 B hit "
+                             "record) streamed every wave" % (st.n_slots * 104 / 1e6, st.n_slots)},
             "msamples_per_s": round(samples_all / span_ms / 1e3, 3),
             "rays": int(rays_all), "rays_per_sample": round(rays_all / samples_all, 4),
             "kernel_ms_per_step": round(kernel_ms / K, 3),

@@ -47,7 +47,7 @@ typedef struct rt_render_params {
   int32_t rng_mode;        /* 0 = Philox4x32-10 (counter based), 1 = reference XORWOW streams, curand_init(1984+pixel,0,0) */
   int32_t split_mode;      /* 0 = tile split (rank owns scanlines j = rank mod world), 1 = spp split */
   int32_t rank, world;     /* this process's share; world <= 0 means 1 */
-  int32_t slots;           /* Philox mode: path slots in flight; <= 0: automatic (8 Mi). Reference-RNG mode: one per pixel */
+  int32_t slots;           /* Philox mode: path slots in flight; <= 0: automatic (32 Mi). Reference-RNG mode: one per pixel */
   int32_t aov;             /* != 0: also produce primary-hit object id / material id / t buffers */
   int32_t accumulate;      /* != 0: progressive pass: the linear sums of this call are ADDED to the accumulation buffer of the
                               previous call (same resolution and split); resolve with rt_resolve(total spp so far) */
