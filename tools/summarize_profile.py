@@ -20,8 +20,8 @@ if os.path.exists(lp):
         name = r[ik].split("(")[0].replace("void ", "").replace("rt::", "")
         agg[name][0] += 1; agg[name][1] += us
     tot = sum(a[1] for a in agg.values())
-    out.append("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, `python tools/prof_cmd.py 12`:\n"
-               "C4 800x800, 12 spp, Philox mode; per-launch times are serialised and cold-cache: compare SHARES)\n")
+    out.append("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, `python tools/prof_cmd.py $SPPN` (tools/gpu_r02.sh ncu; 40 spp since r02v, 12 before):\n"
+               "C4 800x800, Philox mode; per-launch times are serialised and cold-cache: compare SHARES)\n")
     out.append("| kernel | launches | total us | share | mean us |\n|---|---|---|---|---|")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("| %s | %d | %.1f | %.1f%% | %.2f |" % (k, a[0], a[1], 100 * a[1] / tot, a[1] / a[0]))
@@ -86,7 +86,8 @@ if os.path.exists(rep):
                                     "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed") if k in hdr) *
                                num(r[hdr.index("smsp__cycles_elapsed.avg")])) if "smsp__cycles_elapsed.avg" in hdr else None}
         # rays of the launch: a k_trace warp owns RT_RANGE (env, default 64) rays of the dense layout, a k_shade thread one
-        per_thread = (int(os.environ.get("RT_RANGE", "64")) / 32.0) if n.startswith("k_trace") else 1.0
+        # (a k_shade block walks RT_SHADE_ITEMS chunks of its block size: env, default 8)
+        per_thread = (int(os.environ.get("RT_RANGE", "64")) / 32.0) if n.startswith("k_trace") else float(os.environ.get("RT_SHADE_ITEMS", "8"))
         traffic[n]["rays"] = traffic[n]["grid"] * traffic[n]["block"] * per_thread
     json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
     # ---- per-source-line attribution ----
