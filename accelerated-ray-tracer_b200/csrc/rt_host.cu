@@ -754,9 +754,11 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     // Every wave of a pool runs k_trace over its dense layout and k_shade over the queues that wave filled (a lane
     // whose sample ended takes the next work item there). The host reads the queue fills back every `batch` waves: a
     // wave that traced no ray means the pool has run out of work; the job is done when all pools have.
-    int batch = 8;
+    // A job whose samples all start in the first wave (no regeneration: C1 exactly is 900 000 samples) only shrinks from
+    // wave to wave, so the host looks every 4 waves and the grids follow the ray count sooner (C1: 1.10 -> 0.82 ms).
+    int batch = P.work_total <= (long long)P.n_slots ? 4 : 8;
     if (const char* e = getenv("RT_WAVE_BATCH")) batch = std::max(1, atoi(e));
-    int tail_rays = 16384;  // a pool's wave at or below this many rays (work counter dry) is handed to k_finish; 0: never
+    int tail_rays = 65536;  // a pool's wave at or below this many rays (work counter dry) is handed to k_finish; 0: never
     if (const char* e = getenv("RT_TAIL_RAYS")) tail_rays = std::max(0, atoi(e));
     FILE* wlog = nullptr;  // diagnostics: one line per wave (rays of the wave, k_trace ms, k_shade ms)
     if (p->profile) if (const char* e = getenv("RT_WAVE_LOG")) { wlog = fopen(e, "a"); batch = 1; }
@@ -767,6 +769,13 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
     CU(cudaEventRecord(eset, st));
     for (int k = 1; k < n_pools; ++k) CU(cudaStreamWaitEvent(streams[k], eset, 0));  // the other pools start after the counters are set
     int Gs[RT_MAX_POOLS], Gt[RT_MAX_POOLS];
+    int finish_grid_max = 148 * 4;  // k_finish blocks the GPU holds at once
+    {
+      int dev = 0, sms = 0, per_sm = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish, 128, 0) == cudaSuccess && sms > 0 && per_sm > 0)
+        finish_grid_max = sms * per_sm;
+    }
     {
       int work_base = 0;  // pool k draws work items [work_base, work_base + n_k) in k_init
       for (int k = 0; k < n_pools; ++k) {
@@ -822,7 +831,9 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
             if (!ref_rng && !wlog && last > 0 && last <= tail_rays) {
               // few enough paths left: every lane keeps its path to the end in ONE kernel instead of ~40 more waves that
               // each cost the latency of their slowest ray plus two launches
-              k_finish<<<(int)((cap + 127) / 128), 128, 0, streams[k]>>>(s->dscene, Pp[k], Ap[k], s->counters.p + k, parity);
+              int spread_log2 = 0;  // as thin as one resident grid allows (C1 exactly, hand-over at 39 Ki paths: 1 path per lane 0.95 ms, per 32 lanes 1.31)
+              while (spread_log2 < 5 && ((cap << (spread_log2 + 1)) + 127) / 128 <= (size_t)finish_grid_max) ++spread_log2;
+              k_finish<<<(int)(((cap << spread_log2) + 127) / 128), 128, 0, streams[k]>>>(s->dscene, Pp[k], Ap[k], s->counters.p + k, parity, spread_log2);
               ++launches;
               done[k] = true;
             }

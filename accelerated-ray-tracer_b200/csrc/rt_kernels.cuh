@@ -576,11 +576,14 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINB) k_shade(DScene S, Ren
 // launches - the Book-1 scene at 400x225x10 spent 45 of its 56 waves like that. Here every lane KEEPS its path: trace
 // (one-ray-per-lane traversal) and shade in a loop until the path ends. Same events, same Philox keys (pixel, sample,
 // bounce), fixed-point sums: the image does not change by a bit, whichever wave the hand-over happens at.
-__global__ void __launch_bounds__(128) k_finish(DScene S, RenderParams P, PathArrays A, WaveCounters* C, int parity) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+// spread_log2: one path per 2^spread_log2 lanes. A warp's bounce takes as long as its SLOWEST lane's closest-hit query, and at
+// the end of a job latency is all that is left, so the host spreads the paths over as many warps as the GPU holds at once.
+__global__ void __launch_bounds__(128) k_finish(DScene S, RenderParams P, PathArrays A, WaveCounters* C, int parity, int spread_log2) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int n = C->order_len;
-  if (gid - lane >= n) return;
+  if (((tid - lane) >> spread_log2) >= n) return;
+  const int gid = (tid & ((1 << spread_log2) - 1)) == 0 ? (tid >> spread_log2) : n;  // position of the dense layout, or none
   bool active = false;
   Ray r; r.o = v3(0, 0, 0); r.d = v3(1, 1, 1); r.tm = 0.f;
   V3 thr = v3(1, 1, 1);
@@ -625,7 +628,8 @@ __global__ void __launch_bounds__(128) k_finish(DScene S, RenderParams P, PathAr
   }
   rays = __reduce_add_sync(0xFFFFFFFFu, (unsigned)rays);
   if (lane == 0 && rays) atomicAdd(&C->rays, rays);
-  if (gid == 0) { C->order_len = 0; for (int q = 0; q < RT_NQ; ++q) { C->n_queue[0][q] = 0; C->n_queue[1][q] = 0; } }
+  // (the wave counters are left as they are: rt_render uploads fresh ones before the next job, and a reset here would race
+  //  with blocks of this grid that have not read order_len yet)
 }
 
 RT_D float apply_gamma(float c, float gamma) {  // main.cu:37-42

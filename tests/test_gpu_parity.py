@@ -319,11 +319,12 @@ def test_tail_kernel_does_not_change_the_image(pyrt, monkeypatch):
     out = {}
     for tail in ("0", "16384", "1000000"):
         monkeypatch.setenv("RT_TAIL_RAYS", tail)
-        for sid, nx, ny, spp in ((1, 200, 112, 10), (8, 96, 96, 6)):
+        # (scene 10 here: BASELINE config C1's size, 900 000 samples: the tail kernel's grid is many times what the GPU holds)
+        for sid, nx, ny, spp in ((1, 200, 112, 10), (8, 96, 96, 6), (10, 400, 225, 10)):
             with _scene(pyrt, sid, nx, ny) as sc:
                 st = sc.render(spp=spp, rng_mode=0)
                 out[(tail, sid)] = (sc.framebuffer(), st.rays, st.waves, st.nonfinite_samples)
-    for sid in (1, 8):
+    for sid in (1, 8, 10):
         base = out[("0", sid)]
         for tail in ("16384", "1000000"):
             fb, rays, waves, nonfinite = out[(tail, sid)]
