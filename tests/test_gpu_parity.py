@@ -521,7 +521,7 @@ def test_two_gpu_paths_match_single_gpu(pyrt):
     rt_cli --gpus 2 (one process, one host thread per GPU) printing the reference's integers."""
     import subprocess, sys, torch
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (evidence of the last 2-GPU run: profiles/r01f_dist_check_n2.txt)")
+        pytest.skip("needs 2 GPUs (evidence of the last 2-GPU run: profiles/r02f_dist_check_n2.txt, profiles/r02f_pytest_two_gpu.log)")
     root = os.path.dirname(os.path.dirname(__file__))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "dist_check.py")],
