@@ -89,14 +89,39 @@ if os.path.exists(rep):
         # (a k_shade block walks RT_SHADE_ITEMS chunks of its block size: env, default 8)
         per_thread = (int(os.environ.get("RT_RANGE", "64")) / 32.0) if n.startswith("k_trace") else float(os.environ.get("RT_SHADE_ITEMS", "8"))
         traffic[n]["rays"] = traffic[n]["grid"] * traffic[n]["block"] * per_thread
-    json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
     # ---- per-source-line attribution ----
-    sass = os.path.join(G, "elf", "all_%s.sass" % tag)
+    sass = os.path.join(G, "elf", "all_%s.sass" % tag)  # nvdisasm -gi -c of the library's cubin (cuobjdump -xelf all)
+    for kern, pref in (("k_trace", "_ZN2rt7k_trace"), ("k_shade", "_ZN2rt7k_shadeILi0E")):
+        srccsv = os.path.join(G, "src_%s_%s.csv" % (kern, tag))
+        with open(srccsv, "w") as f:
+            subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern, "--launch-count", "1",
+                            "--print-source", "sass"], stdout=f, text=True)
+        # the sass_thread_inst_executed_op_f* counters do not see the packed f32x2 instructions (FADD2 / FMUL2 / FFMA2,
+        # two IEEE operations per lane): count them from the SASS page and add them to the launch's flop
+        rows = list(csv.reader(open(srccsv)))
+        if len(rows) > 2 and "Source" in rows[1] and "Thread Instructions Executed" in rows[1]:
+            isrc, ithr = rows[1].index("Source"), rows[1].index("Thread Instructions Executed")
+            packed = 0.0
+            first_addr = rows[2][0] if len(rows) > 2 else None
+            for k, r in enumerate(rows[2:]):
+                if k > 0 and r and r[0] == first_addr:
+                    break  # the page lists every captured launch of the kernel one after the other: the first one only
+                if len(r) <= max(isrc, ithr):
+                    continue
+                op = r[isrc].split()[1] if r[isrc].lstrip().startswith("@") and len(r[isrc].split()) > 1 else (r[isrc].split() or [""])[0]
+                if op.startswith(("FADD2", "FMUL2")):
+                    packed += 2.0 * float(r[ithr] or 0)
+                elif op.startswith("FFMA2"):
+                    packed += 4.0 * float(r[ithr] or 0)
+            key = kern if kern in traffic else (kern + "<0>")
+            if key in traffic and traffic[key].get("flop") is not None:
+                traffic[key]["flop_scalar_counters"] = traffic[key]["flop"]
+                traffic[key]["flop_packed_f32x2"] = packed
+                traffic[key]["flop"] += packed
+    json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
     if os.path.exists(sass):
-        for kern, pref in (("k_trace", "_ZN2rt7k_traceILi0E"), ("k_shade", "_ZN2rt7k_shadeILi0E")):
+        for kern, pref in (("k_trace", "_ZN2rt7k_trace"), ("k_shade", "_ZN2rt7k_shadeILi0E")):
             srccsv = os.path.join(G, "src_%s_%s.csv" % (kern, tag))
-            with open(srccsv, "w") as f:
-                subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], stdout=f, text=True)
             t = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), srccsv, sass, pref, "30"], stdout=subprocess.PIPE, text=True).stdout
             out.append("## %s: stall samples and instructions by source line (deepest inline frame outside rt_math.h / rng.h)\n\n```\n%s```\n" % (kern, t))
 open(os.path.join(P, "%s_ncu_summary.md" % tag), "w").write("# ncu summary %s\n\n" % tag + "\n".join(out) + "\n")
