@@ -236,9 +236,9 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
         }
         const int g = next + __popc(mfin & lt);
         if (g < end) {
-          const float4 d = ray_d[g];
+          const float4 d = ray_d[g], o = ray_o[g];  // both at once: one round trip (a hole's origin is allocated, never used).
+                                                    // Prefetching the range's second half here: -2 % (A/B r02zz)
           if (__float_as_int(d.w) >= 0) {
-            const float4 o = ray_o[g];
             Ray r; r.o = v3(o.x, o.y, o.z); r.d = v3(d.x, d.y, d.z); r.tm = o.w;
             T.begin(r, tmin, FLT_MAX);
             gid = g;
@@ -249,12 +249,6 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       }
       if (next >= end) break;  // everyone finished and the range is drained
       next += __popc(mfin);
-#ifdef RT_PREFETCH  // A/B on C4: no gain (the refill of a 64-ray range happens once)
-      if (next + lane < end) {  // the rays the next refill will take: start their way up from HBM / L2 now
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(ray_d + next + lane));
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(ray_o + next + lane));
-      }
-#endif
       continue;
     }
     const bool can = T.can_expand();
