@@ -4,7 +4,7 @@ set -uo pipefail
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O; TAG=${1:-ab3}
 timeout 900 python -m pytest tests -q -m gpu -x -k "not converged" > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log
-[[ -x tools/scratch/packed_bench ]] && tools/scratch/packed_bench | tee $O/packed_bench_$TAG.json
+[[ -x tools/packed_bench ]] && tools/packed_bench | tee $O/packed_bench_$TAG.json
 [[ -f accelerated-ray-tracer_b200/lib/variants/stats.so ]] && python tools/stats_cmd.py 40 | tee $O/stats_$TAG.txt
 for cfg in "300 9 800 800" "200 8 600 600" "16 1 3840 2160 500" "100 1 1200 600"; do
   echo "== cfg $cfg shipped"; python tools/prof_cmd.py $cfg; python tools/prof_cmd.py $cfg
