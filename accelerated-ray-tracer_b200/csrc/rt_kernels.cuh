@@ -217,6 +217,24 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
   T.reset();
   bool flush = false;  // warp-uniform: a deferred media list is nearly full
   while (true) {
+#if RT_REFILL_MIN >= 32
+    // The warp refills when ALL its lanes are done, and that is exactly when no lane can expand a node and no lane has a leaf
+    // pending: the two ballots the phase choice needs anyway say so (no ballot of finished lanes, no range test per turn).
+    const bool can = T.can_expand();
+    const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
+    const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, T.nl > 0);
+    const bool refill = (mexp | mleaf) == 0u;
+    const bool fin = refill;
+    const unsigned mfin = 0xFFFFFFFFu;
+    // media phase: the deferred media, before the hits are stored (or right away when a list is nearly full)
+    if (flush || refill) {
+      if (flush || __any_sync(0xFFFFFFFFu, T.nm > 0)) {
+        T.media_phase(S, m_mq_tlp, m_mq_tn, true);
+        flush = false;
+        continue;
+      }
+    }
+#else
     const bool fin = T.finished();
     const unsigned mfin = __ballot_sync(0xFFFFFFFFu, fin);
     const bool refill = mfin == 0xFFFFFFFFu || (next < end && __popc(mfin) >= RT_REFILL_MIN);
@@ -226,6 +244,7 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       flush = false;
       continue;
     }
+#endif
     if (refill) {
       // ---------------- refill: finished lanes store their hit and take the next rays of the range ----------------
       if (fin) {
@@ -251,14 +270,16 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       next += __popc(mfin);
       continue;
     }
+#if RT_REFILL_MIN < 32
     const bool can = T.can_expand();
     const unsigned mexp = __ballot_sync(0xFFFFFFFFu, can);
     const unsigned mleaf = __ballot_sync(0xFFFFFFFFu, T.nl > 0);
+#endif
     const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have() && T.nl > 0);  // traversal done, leaves pending
     if (Trav::pick_node_phase(mexp, mleaf, mwait)) {
       if (lane == 0) RT_COUNT(4, 1);
 #ifdef RT_STATS
-      { const unsigned mblk = __ballot_sync(0xFFFFFFFFu, T.have() && !can); if (lane == 0) { atomicAdd(&g_stats2[0], (unsigned long long)__popc(mfin)); atomicAdd(&g_stats2[1], (unsigned long long)__popc(mblk)); atomicAdd(&g_stats2[2], (unsigned long long)__popc(mexp)); } }
+      { const unsigned mblk = __ballot_sync(0xFFFFFFFFu, T.have() && !can); const unsigned mfin_s = __ballot_sync(0xFFFFFFFFu, T.finished()); if (lane == 0) { atomicAdd(&g_stats2[0], (unsigned long long)__popc(mfin_s)); atomicAdd(&g_stats2[1], (unsigned long long)__popc(mblk)); atomicAdd(&g_stats2[2], (unsigned long long)__popc(mexp)); } }
 #endif
       if (can) T.node_step(S, &C->overflow, RT_TRAV_ARGS(m));
     } else {
