@@ -3,7 +3,7 @@
 import re, sys
 cfg = var = None; res = {}
 for l in open(sys.argv[1]):
-    m = re.match(r'== cfg (.*?) (shipped|accel\S+)', l)
+    m = re.match(r'== cfg (.*?) (shipped|accel\S+|env:\S+)', l)
     if m: cfg = m.group(1); var = m.group(2).split('/')[-1]; continue
     m = re.search(r'([\d.]+) Mrays/s', l)
     if m and cfg: res.setdefault(cfg, {}).setdefault(var, []).append(float(m.group(1)))
