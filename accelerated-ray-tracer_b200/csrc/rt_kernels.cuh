@@ -7,15 +7,18 @@
 //
 //   k_init     the first n_slots camera samples (render_init + main.cu:119-123); reference-RNG mode: XORWOW seeding
 //   k_trace    pure closest-hit kernel (main.cu:57; bvh.cuh:95). A WARP owns RT_RANGE consecutive rays of the wave's
-//              dense layout and runs them through the 4-wide BVH with lane refill: a lane whose ray is finished takes
-//              the next ray of the warp's range, so the warp-wide node / leaf phases stay full until the range is
-//              drained. No block-level barrier anywhere. At the end the warp bins its rays by the material class of
+//              dense layout and runs them through the 4-wide BVH 32 at a time, in warp-wide node / leaf / media phases
+//              (rt_intersect.cuh); when all 32 are done the lanes store their hits and take the range's next 32 rays.
+//              No block-level barrier anywhere. At the end the warp bins its rays by the material class of
 //              the hit into shade queues (one atomic per class per warp, spread over RT_NSUB sub-queues).
 //   k_shade    one material class per warp, reading the path state in queue order (neighbouring entries were written
 //              by neighbouring trace lanes): miss/background, emission, scatter, throughput (main.cu:58-83). A finished
 //              sample is added to its pixel and the lane takes the NEXT camera sample right away (path regeneration,
 //              main.cu:119-124); the new state is written densely at the thread's own position of the other
-//              ping-pong set, which is the layout the next k_trace walks.
+//              ping-pong set, which is the layout the next k_trace walks. A block walks RT_SHADE_ITEMS chunks of
+//              queue positions with the next chunk's loads in flight, and a warp reserves the work items of all its
+//              miss / light lanes with one atomic.
+//   k_finish   the tail of a job: the last few ten thousand paths are run to their end in one kernel
 //   k_accumulate / k_resolve   sums -> linear accumulation buffer -> 1/ns, gamma     (main.cu:128-132)
 //   k_aov      primary-hit object/material id + t for the centre ray of every pixel
 //
