@@ -317,3 +317,60 @@ def test_c5_grid_generator_sizes(pyrt):
         assert (kinds == 0).all()  # spheres only
         moving = (np.abs(sd.obj["dc"][sd.top]).sum(axis=1) > 0).mean()
         assert 0.6 < moving < 0.9  # ~80% of the grid is diffuse (moving), SURVEY §8a7
+
+
+def test_scene_builder_bvh_node_matches_python_builder_and_flattens(pyrt, tmp_path):
+    """The source-level API (csrc/scene_builder.h): a C++ program builds translate(rotate_y(bvh_node(spheres))) + with_material
+    of the same group with rt::SceneBuilder and writes the SD; the numpy builder of tests/sdgen.py builds the same scene.
+    Same object graph (floats bit for bit, boxes included) and the same flattening through rt_sd_flatten."""
+    csrc = os.path.join(ROOT, "accelerated-ray-tracer_b200", "csrc")
+    src = tmp_path / "g.cpp"
+    src.write_text(r'''
+#include <cmath>
+#include <cstdio>
+#include "scene_builder.h"
+using namespace rt;
+struct HM : DevMath { float sinf_(float x) override { return sinf(x); } float cosf_(float x) override { return cosf(x); }
+                      float tanf_(float x) override { return tanf(x); } };
+int main(int, char** argv) {
+  HM dm; SceneDesc sd; sd.nx = 64; sd.ny = 48;
+  SceneBuilder B(sd, dm);
+  const int grey = B.lambertian(v3(0.5f, 0.5f, 0.5f)), gold = B.metal(v3(0.8f, 0.6f, 0.2f), 0.25f);
+  std::vector<int> members;
+  for (int i = 0; i < 5; ++i) members.push_back(B.sphere(v3(0.75f * i + 0.25f, 0.5f, -0.25f * i - 0.5f), 0.3f, grey));
+  members.push_back(B.translate(B.sphere(v3(0.5f, 0.75f, 0.5f), v3(0.5f, 1.0f, 0.5f), 0.25f, gold), v3(1.0f, 0.0f, 1.5f)));  // a moving sphere, instanced
+  const int g = B.bvh_node(members);
+  B.add(B.translate(B.rotate_y(g, 0.0f), v3(-2.0f, 1.0f, 0.5f)));   // 0 degrees: sin / cos are exact on every libm
+  B.add(B.with_material(g, gold));
+  B.add(B.sphere(v3(0, -100.5f, 0), 100.0f, grey));
+  B.camera(v3(0, 2, 8), v3(0, 1, 0), v3(0, 1, 0), 40.0f, 64.0f / 48.0f, 0.0f, 8.0f, 0.0, 1.0);
+  const std::string bin = sd_serialize(sd);
+  FILE* f = fopen(argv[1], "wb"); fwrite(bin.data(), 1, bin.size(), f); fclose(f);
+  return 0;
+}
+''')
+    exe = tmp_path / "g"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I", csrc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                           os.path.join(csrc, "scene_builder.cpp"), os.path.join(csrc, "generators.cpp"), os.path.join(csrc, "jpeg_baseline.cpp")])
+    out = tmp_path / "scene.sd"
+    subprocess.check_call([str(exe), str(out)])
+    cpp = pyrt.SD(out.read_bytes())
+    sys.path.insert(0, os.path.dirname(__file__))
+    from sdgen import SDBuilder
+    P = SDBuilder(64, 48)
+    grey, gold = P.lambertian(P.solid((0.5, 0.5, 0.5))), P.metal((0.8, 0.6, 0.2), 0.25)
+    members = [P.sphere((0.75 * i + 0.25, 0.5, -0.25 * i - 0.5), 0.3, grey) for i in range(5)]
+    members.append(P.translate(P.sphere((0.5, 0.75, 0.5), 0.25, gold, c1=(0.5, 1.0, 0.5)), (1.0, 0.0, 1.5)))
+    g = P.bvh(members)
+    P.add(P.translate(P.rotate_y(g, 0.0), (-2.0, 1.0, 0.5)))
+    P.add(P.with_material(g, gold))
+    P.add(P.sphere((0, -100.5, 0), 100.0, grey))
+    P.camera((0, 2, 8), (0, 1, 0), (0, 1, 0), 40.0, 0.0, 8.0)
+    py = pyrt.SD(P.to_bytes())
+    assert cpp.top_keys() == py.top_keys()
+    fc, oc = pyrt.sd_flatten(out.read_bytes())
+    fp, op = pyrt.sd_flatten(P.to_bytes())
+    assert list(oc) == list(op) == [0] * 6 + [1] * 6 + [2]
+    assert fc.top_keys() == fp.top_keys()
+    kinds = [int(fc.obj["kind"][t]) for t in fc.top]
+    assert kinds == [3] * 6 + [6] * 6 + [0]   # translate(rotate_y(member)) x 6, with_material(member) x 6, the ground sphere
