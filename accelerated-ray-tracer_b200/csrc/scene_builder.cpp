@@ -305,6 +305,47 @@ void SceneBuilder::camera(V3 lookfrom, V3 lookat, V3 vup, float vfov, float aspe
 }
 
 // ---- reference leaf order: replay of bvh_node's constructor (bvh.cuh:29-84) on indices ----
+// The reference sorts every range with a selection sort (bvh.cuh:46-81): position i receives the FIRST smallest key of
+// [i, end) (strict <) and the element that was at i moves to where that one came from. The permutation it leaves
+// matters only among equal keys (a grid of boxes has many), and it is not the stable one. Long ranges replay exactly
+// these swaps through a tournament tree over the positions (leftmost minimum, two leaf updates per step):
+// O(n log n) instead of O(n^2) per range - 10 004 spheres: 0.75 s -> a few ms of rt_build_scene.
+static void selection_sort_replay(std::vector<int>& objs, const SceneDesc& sd, int start, int end, int axis) {
+  const int n = end - start;
+  if (n < 48) {  // the reference's loop as it stands
+    for (int i = start; i < end - 1; ++i) {
+      int best = i;
+      for (int j = i + 1; j < end; ++j)
+        if (sd.obj[objs[j]].box_min[axis] < sd.obj[objs[best]].box_min[axis]) best = j;
+      if (best != i) std::swap(objs[i], objs[best]);
+    }
+    return;
+  }
+  std::vector<float> key((size_t)n);
+  for (int p = 0; p < n; ++p) key[p] = sd.obj[objs[start + p]].box_min[axis];
+  int sz = 1;
+  while (sz < n) sz <<= 1;
+  std::vector<int> tr((size_t)2 * sz, -1);  // per node: position of the leftmost minimum of its span, -1: nothing left
+  auto better = [&](int a, int b) {         // a lies left of b: b wins only with a strictly smaller key
+    if (a < 0) return b;
+    if (b < 0) return a;
+    return key[b] < key[a] ? b : a;
+  };
+  for (int p = 0; p < n; ++p) tr[sz + p] = p;
+  for (int k = sz - 1; k >= 1; --k) tr[k] = better(tr[2 * k], tr[2 * k + 1]);
+  auto fix = [&](int p) { for (int k = (sz + p) >> 1; k >= 1; k >>= 1) tr[k] = better(tr[2 * k], tr[2 * k + 1]); };
+  for (int i = 0; i < n - 1; ++i) {
+    const int best = tr[1];  // positions < i have been removed: the leftmost minimum of [i, n)
+    if (best != i) {
+      std::swap(objs[start + i], objs[start + best]);
+      std::swap(key[i], key[best]);
+      fix(best);
+    }
+    tr[sz + i] = -1;
+    fix(i);
+  }
+}
+
 static void bvh_order_rec(std::vector<int>& objs, const SceneDesc& sd, int start, int end) {
   const int n = end - start;
   if (n <= 1) return;
@@ -317,12 +358,7 @@ static void bvh_order_rec(std::vector<int>& objs, const SceneDesc& sd, int start
   int axis = 0;
   if (sy > sx && sy >= sz) axis = 1;
   else if (sz > sx && sz >= sy) axis = 2;
-  for (int i = start; i < end - 1; ++i) {  // the reference's selection sort, swaps included
-    int best = i;
-    for (int j = i + 1; j < end; ++j)
-      if (sd.obj[objs[j]].box_min[axis] < sd.obj[objs[best]].box_min[axis]) best = j;
-    if (best != i) std::swap(objs[i], objs[best]);
-  }
+  selection_sort_replay(objs, sd, start, end, axis);
   const int mid = start + (n >> 1);
   bvh_order_rec(objs, sd, start, mid);
   bvh_order_rec(objs, sd, mid, end);

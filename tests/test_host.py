@@ -374,3 +374,15 @@ int main(int, char** argv) {
     assert fc.top_keys() == fp.top_keys()
     kinds = [int(fc.obj["kind"][t]) for t in fc.top]
     assert kinds == [3] * 6 + [6] * 6 + [0]   # translate(rotate_y(member)) x 6, with_material(member) x 6, the ground sphere
+
+
+def test_leaf_order_replay_equals_the_reference_selection_sort(tmp_path):
+    """reference_leaf_order replays bvh_node's constructor (bvh.cuh:29-84) to know the reference's leaf order (exact-t ties are
+    broken by it). Long ranges replay the selection sort's swaps through a tournament tree; tests/cpp/leaf_order_replay.cpp
+    checks that against the plain O(n^2) loop on 300 random / tie-heavy key sets."""
+    csrc = os.path.join(ROOT, "accelerated-ray-tracer_b200", "csrc")
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", csrc, "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "cpp", "leaf_order_replay.cpp"), os.path.join(csrc, "jpeg_baseline.cpp")])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert "sorttest: 0 mismatches" in out
