@@ -348,6 +348,32 @@ def test_philox_is_deterministic_and_seed_dependent(pyrt):
     assert np.array_equal(a.view(np.uint32), d.view(np.uint32))  # fixed-point sums: independent of the slot count
 
 
+def test_full_size_c4_image_does_not_depend_on_the_schedule(pyrt, monkeypatch):
+    """BASELINE config C4 at its FULL resolution (800x800, 24 samples per pixel = 15 M samples, 74 M rays), through properties
+    that hold at any size: the image and the ray count of the counter-based mode are functions of (seed, pixel, sample,
+    bounce) alone, so they do not move by a bit with the number of paths in flight, the number of path pools, the host's
+    check interval, the hand-over to the tail kernel, or a split of the sample numbers into two progressive passes."""
+    with _scene(pyrt, 9, 800, 800) as sc:
+        st = sc.render(spp=24, rng_mode=0)
+        base, rays = sc.framebuffer(), st.rays
+        assert st.nonfinite_samples == 0 and st.stack_overflow == 0 and st.samples == 800 * 800 * 24
+        assert abs(rays / st.samples - 4.84) < 0.03   # the reference's counted bounce loop: 4.8418 rays per sample on this scene
+        for env in ({"RT_POOLS": "1"}, {"RT_POOLS": "3", "RT_WAVE_BATCH": "1"}, {"RT_TAIL_RAYS": "0"}, {"RT_TAIL_RAYS": "3000000"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            st2 = sc.render(spp=24, rng_mode=0, slots=1000000 if "RT_POOLS" in env else 0)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert st2.rays == rays, env
+            assert np.array_equal(sc.framebuffer().view(np.uint32), base.view(np.uint32)), env
+        # two passes of 12 sample numbers each, accumulated (spp split by hand) = one pass of 24, to float-sum rounding
+        sc.render(spp=24, rng_mode=0, split_mode=1, rank=0, world=2)
+        st3 = sc.render(spp=24, rng_mode=0, split_mode=1, rank=1, world=2, accumulate=True)
+        sc.resolve(total_spp=24)
+        two = sc.framebuffer()
+    assert np.allclose(two, base, rtol=2e-6, atol=1e-6)
+
+
 def test_scale_up_c5_bvh_matches_brute_force_ids(pyrt, built):
     """C5 shape (bouncing grid scaled to ~10k spheres): the device-built BVH returns the same primary hits as the
     CPU oracle's brute-force scan over all objects."""
