@@ -374,6 +374,31 @@ def test_full_size_c4_image_does_not_depend_on_the_schedule(pyrt, monkeypatch):
     assert np.allclose(two, base, rtol=2e-6, atol=1e-6)
 
 
+def test_full_size_c5_tile_split_and_builders_agree(pyrt, monkeypatch):
+    """BASELINE config C5 at its FULL resolution (3840x2160) on 99 860 spheres, through size-independent properties: the
+    interleaved-scanline tile split over 3 ranks assembles to the bits of the one-rank image with the same total ray
+    count, and the image does not depend on which device BVH builder made the tree (PLOC or the plain radix tree)."""
+    out = {}
+    for builder in ("ploc", "lbvh"):
+        monkeypatch.setenv("RT_BVH_BUILDER", builder)
+        with _scene(pyrt, 1, 3840, 2160, grid_half=158) as sc:
+            assert sc.info.n_top == 99860
+            st = sc.render(spp=2, rng_mode=0)
+            assert st.nonfinite_samples == 0 and st.stack_overflow == 0
+            out[builder] = (sc.framebuffer(), st.rays)
+            if builder == "ploc":
+                parts, rays = [], 0
+                for r in range(3):
+                    st_r = sc.render(spp=2, rng_mode=0, rank=r, world=3, split_mode=0)
+                    parts.append(sc.framebuffer()); rays += st_r.rays
+                full = pyrt.assemble_rows(parts, 2160)
+                assert rays == st.rays
+                assert np.array_equal(full.view(np.uint32), out["ploc"][0].view(np.uint32))
+    monkeypatch.delenv("RT_BVH_BUILDER")
+    assert out["ploc"][1] == out["lbvh"][1]
+    assert np.array_equal(out["ploc"][0].view(np.uint32), out["lbvh"][0].view(np.uint32))
+
+
 def test_scale_up_c5_bvh_matches_brute_force_ids(pyrt, built):
     """C5 shape (bouncing grid scaled to ~10k spheres): the device-built BVH returns the same primary hits as the
     CPU oracle's brute-force scan over all objects."""
