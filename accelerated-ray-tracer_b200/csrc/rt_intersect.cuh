@@ -406,9 +406,6 @@ struct Trav {
   RT_D void node_step(const DScene& S, unsigned int* overflow, uint32_t* stack, uint32_t* lq_ref, uint32_t* lq_tlp, float* lq_tn) {
     RT_COUNT(0, 1);
     const float4* np = reinterpret_cast<const float4*>(S.nodes + cur);
-#ifdef RT_NODE_PREFETCH
-    const bool big = S.n_nodes > RT_NODE_PREFETCH;  // warp-uniform
-#endif
     // aabb::hit (aabb.cuh:45-61): t0 = (min - o) * invD, t1 = (max - o) * invD, swapped when invD < 0. The swap is
     // done by the LOAD: per-ray offsets pick the near / far plane vectors of the node, no per-child selects.
     // float4 index of the NEAR plane vector of each axis inside a node (lox 0, loy 1, loz 2, hix 3, hiy 4, hiz 5)
@@ -459,9 +456,6 @@ struct Trav {
         const uint32_t i = key[k] & 3u;
         const uint32_t c = (i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0]);
         stack[sp++] = c & 0x7FFFFFFFu;
-#ifdef RT_NODE_PREFETCH  // big scenes (nodes in L2 / HBM, not L1): start the deferred child's line on its way now
-        if (big) asm volatile("prefetch.global.L1 [%0];" :: "l"(S.nodes + (c & 0x7FFFFFFFu)));
-#endif
       }
     }
     uint32_t next = RT_NODE_EMPTY;
