@@ -26,4 +26,4 @@ if [[ $WHAT == *c5* ]]; then
     echo "bench c5-1m n=$n rc=$?"; cut -c1-500 $O/bench_n${n}_c5_1m_$TAG.json
   done
 fi
-tail -5 $O/bench_n$N.err
+[[ -f $O/bench_n$N.err ]] && tail -5 $O/bench_n$N.err; true
