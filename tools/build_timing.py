@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "accelerated-ray-tracer_b200")); sys.path.
 import pyrt
 from bench import texture_dir
 pyrt.Scene(7, 64, 64).close()  # CUDA context + module load
-for name, sid, nx, ny, gh in (("C1", 1, 400, 225, 0), ("C4", 9, 800, 800, 0), ("C5-10k", 1, 3840, 2160, 50), ("C5-100k", 1, 3840, 2160, 158)):
+for name, sid, nx, ny, gh in (("C1", 1, 400, 225, 0), ("C4", 9, 800, 800, 0), ("C5-10k", 1, 3840, 2160, 50), ("C5-100k", 1, 3840, 2160, 158), ("C5-1M", 1, 3840, 2160, 500)):
     ts = []
     for i in range(4):
         t0 = time.perf_counter(); sc = pyrt.Scene(sid, nx, ny, grid_half=gh, texture_dir=texture_dir()); t1 = time.perf_counter()
