@@ -414,9 +414,11 @@ struct Trav {
     const float4 nyp = __ldg(np + ony), fyp = __ldg(np + (5 - ony));
     const float4 nzp = __ldg(np + onz), fzp = __ldg(np + (7 - onz));
     const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+#ifdef RT_NO_PACKED_SLAB
     const float ax[4] = {nxp.x, nxp.y, nxp.z, nxp.w}, bx[4] = {fxp.x, fxp.y, fxp.z, fxp.w};
     const float ay[4] = {nyp.x, nyp.y, nyp.z, nyp.w}, by[4] = {fyp.x, fyp.y, fyp.z, fyp.w};
     const float az[4] = {nzp.x, nzp.y, nzp.z, nzp.w}, bz[4] = {fzp.x, fzp.y, fzp.z, fzp.w};
+#endif
     const uint32_t cr[4] = {ch.x, ch.y, ch.z, ch.w};
     uint32_t key[4];  // interior children that are entered: (entry distance bits, child slot); else 0xFFFFFFFF
 #ifndef RT_NO_PACKED_SLAB
