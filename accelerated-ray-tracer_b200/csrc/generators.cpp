@@ -40,9 +40,9 @@ float aspect_of(int nx, int ny) { return fdiv((float)nx, (float)ny); }
 // main.cu:160-244 (grid_half = 11 in the reference; larger for the C5 scale-up)
 void world_bouncing(SceneBuilder& B, int nx, int ny, int grid_half) {
   SceneRng R;
-  {  // one object, material and (mostly) texture per grid cell: no vector regrowth at the C5 scale-up sizes
+  {  // one object, material and (mostly) texture per grid cell: no vector regrowth at the C5 scale-up sizes, huge pages
     const size_t cells = (size_t)4 * grid_half * grid_half + 8;
-    B.S.obj.reserve(cells); B.S.mat.reserve(cells); B.S.tex.reserve(cells); B.S.top.reserve(cells);
+    big_reserve(B.S.obj, cells); big_reserve(B.S.mat, cells); big_reserve(B.S.tex, cells); big_reserve(B.S.top, cells);
   }
   const V3 UT_ORANGE = v3(1.0f, 0.51f, 0.0f);
   int checker = B.checker_texture(0.64f, B.solid_color(v3(1.0f, 1.0f, 1.0f)), B.solid_color(UT_ORANGE));

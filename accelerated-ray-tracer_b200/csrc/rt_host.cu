@@ -321,9 +321,13 @@ static int upload_scene(rt_scene* s) {
   const SceneDesc& sd = s->flat();
   Flattener F(sd);
   const int n = (int)sd.top.size();
-  std::vector<DTlp> tlp(n);
-  std::vector<BuildBox> boxes(n);
-  std::vector<uint32_t> refs(n);
+  {
+    size_t n_sph = 0;
+    for (const auto& o : sd.obj) n_sph += o.kind == RT_OBJ_SPHERE;
+    big_reserve(F.spheres, n_sph);
+  }
+  std::vector<DTlp> tlp; std::vector<BuildBox> boxes; std::vector<uint32_t> refs;
+  big_resize(tlp, (size_t)n); big_resize(boxes, (size_t)n); big_resize(refs, (size_t)n);
   for (int k = 0; k < n; ++k) {
     const rt_object_desc& o = sd.obj[sd.top[k]];
     tlp[k].ref = F.flatten(sd.top[k]);
@@ -340,7 +344,7 @@ static int upload_scene(rt_scene* s) {
     for (int a = 0; a < 3; ++a) { boxes[k].mn[a] = o.box_min[a]; boxes[k].mx[a] = o.box_max[a]; }
   }
   if (F.bad) return fail("upload_scene: a group (bvh_node) where only geometry can be");
-  std::vector<DMat> mats(sd.mat.size());
+  std::vector<DMat> mats; big_resize(mats, sd.mat.size());
   for (size_t i = 0; i < sd.mat.size(); ++i) {
     const rt_material_desc& m = sd.mat[i];
     DMat d; memset(&d, 0, sizeof(d));
@@ -348,7 +352,7 @@ static int upload_scene(rt_scene* s) {
     d.needs_uv = tex_needs_uv(sd, m.tex) ? 1 : 0;
     mats[i] = d;
   }
-  std::vector<DTex> texs(sd.tex.size());
+  std::vector<DTex> texs; big_resize(texs, sd.tex.size());
   for (size_t i = 0; i < sd.tex.size(); ++i) {
     const rt_texture_desc& t = sd.tex[i];
     DTex d; memset(&d, 0, sizeof(d));

@@ -8,12 +8,24 @@
 //     Example: create_world_bouncing's camera v.y is 0.98894989490509 (folded) and not
 //     0.98894983530045 (fused). The `folded` flag selects this regime.
 #include "scene_builder.h"
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
 
 namespace rt {
+
+void advise_huge(void* p, size_t bytes) {
+#if defined(__linux__)
+  const uintptr_t a = ((uintptr_t)p + 4095) & ~(uintptr_t)4095, e = ((uintptr_t)p + bytes) & ~(uintptr_t)4095;
+  if (p && bytes >= ((size_t)8 << 20) && e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
+#else
+  (void)p; (void)bytes;
+#endif
+}
 
 static void put3(float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
 static V3 get3(const float* d) { return v3(d[0], d[1], d[2]); }

@@ -40,6 +40,12 @@ struct HostImage {
   bool valid() const { return !px.empty() && width > 0 && height > 0 && bpp >= 3; }
 };
 
+// Large host arrays (the C5 scale-up scenes: 10^6 objects, ~0.5 GB of descriptions and device tables) spend most of their
+// time in the first touch of fresh memory: ask for huge pages before that touch where the kernel hands them out on request.
+void advise_huge(void* p, size_t bytes);
+template <class T> void big_reserve(std::vector<T>& v, size_t n) { v.reserve(n); advise_huge(v.data(), n * sizeof(T)); }
+template <class T> void big_resize(std::vector<T>& v, size_t n) { big_reserve(v, n); v.resize(n); }
+
 struct SceneDesc {
   int scene_id = 0, nx = 0, ny = 0;
   std::vector<rt_texture_desc> tex;
