@@ -234,6 +234,9 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       if (flush || __any_sync(0xFFFFFFFFu, T.nm > 0)) {
         T.media_phase(S, m_mq_tlp, m_mq_tn, true);
         flush = false;
+#ifdef RT_STACK_CULL
+        T.revalidate(m_stack);
+#endif
         continue;
       }
     }
@@ -245,6 +248,9 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
     if (flush || (refill && __any_sync(0xFFFFFFFFu, fin && T.nm > 0))) {
       T.media_phase(S, m_mq_tlp, m_mq_tn, flush || fin);
       flush = false;
+#ifdef RT_STACK_CULL
+      T.revalidate(m_stack);
+#endif
       continue;
     }
 #endif
@@ -288,6 +294,9 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
     } else {
       if (lane == 0) RT_COUNT(5, 1);
       flush = T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn, m_mq_tlp, m_mq_tn);
+#ifdef RT_STACK_CULL
+      T.revalidate(m_stack);
+#endif
     }
   }
 #if RT_RANGE <= 64
