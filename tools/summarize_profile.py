@@ -71,7 +71,7 @@ if os.path.exists(rep):
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         traffic[n] = {"dram_bytes": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
                       "grid": int(num(r[hdr.index("launch__grid_size")])), "block": int(num(r[hdr.index("launch__block_size")])),
-                      "duration_us": num(r[hdr.index("gpu__time_duration.sum")]) / (1000.0 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1.0),
+                      "duration_us": num(r[hdr.index("gpu__time_duration.sum")]) * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(units[hdr.index("gpu__time_duration.sum")], 1.0),
                       "inst_issued_pct_of_peak": num(r[hdr.index("sm__inst_issued.avg.pct_of_peak_sustained_active")]) if "sm__inst_issued.avg.pct_of_peak_sustained_active" in hdr else None,
                       "threads_per_instruction": num(r[hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")]),
                       "l1_hit_pct": num(r[hdr.index("l1tex__t_sector_hit_rate.pct")]), "l2_hit_pct": num(r[hdr.index("lts__t_sector_hit_rate.pct")]),
@@ -114,6 +114,22 @@ if os.path.exists(rep):
                 elif op.startswith("FFMA2"):
                     packed += 4.0 * float(r[ithr] or 0)
             key = kern if kern in traffic else (kern + "<0>")
+            # k_trace: the rays of the launch are the threads that executed the store of a traced ray's hit (the first
+            # STG.E.64 of the kernel, rt_kernels.cuh `hit[gid] = ...`; the second one marks holes of the dense layout).
+            # grid x block x 2 counts holes and the warps beyond order_len as rays (a late wave of a short job: 3x too many).
+            if kern == "k_trace" and key in traffic:
+                first = True
+                for k, r in enumerate(rows[2:]):
+                    if k > 0 and r and r[0] == first_addr:
+                        break
+                    if len(r) > max(isrc, ithr) and "STG.E.64" in r[isrc]:
+                        if first:
+                            traffic[key]["rays_upper_bound_grid"] = traffic[key]["rays"]
+                            traffic[key]["rays"] = float(r[ithr] or 0)
+                            first = False
+                        else:
+                            traffic[key]["holes"] = float(r[ithr] or 0)
+                            break
             if key in traffic and traffic[key].get("flop") is not None:
                 traffic[key]["flop_scalar_counters"] = traffic[key]["flop"]
                 traffic[key]["flop_packed_f32x2"] = packed
