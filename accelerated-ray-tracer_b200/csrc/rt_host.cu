@@ -793,6 +793,11 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
       }
     }
     int parity = 0;
+    // A BVH of a handful of nodes (the Cornell boxes: 3) has no stack entries worth dropping: the trace kernel without that check
+    // (same hits, same ray count; RT_CULL_MIN_NODES in the environment for A/B and for the test that the image does not depend on it)
+    int cull_min_nodes = RT_CULL_MIN_NODES;
+    if (const char* e = getenv("RT_CULL_MIN_NODES")) cull_min_nodes = atoi(e);
+    const bool small_bvh = s->n_nodes < cull_min_nodes;
     bool done[RT_MAX_POOLS];
     for (int k = 0; k < RT_MAX_POOLS; ++k) done[k] = k >= n_pools;
     auto all_done = [&]() { bool d = true; for (int k = 0; k < n_pools; ++k) d = d && done[k]; return d; };
@@ -803,8 +808,10 @@ extern "C" int rt_render(rt_scene* s, const rt_render_params* p, double* device_
           cudaStream_t sk = streams[k];
           WaveCounters* Ck = s->counters.p + k;
           if (p->profile) CU(cudaEventRecord(pev[3 * w], sk));
-          k_trace<<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, P.tmin, Ap[k].ray_o[parity], Ap[k].ray_d[parity], Ap[k].hit, Ap[k].queues,
-                                               Ap[k].subcap, Ck, parity);
+          if (small_bvh) k_trace_small<<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, P.tmin, Ap[k].ray_o[parity], Ap[k].ray_d[parity], Ap[k].hit,
+                                                                    Ap[k].queues, Ap[k].subcap, Ck, parity);
+          else k_trace<<<Gt[k], RT_TBLOCK, 0, sk>>>(s->dscene, P.tmin, Ap[k].ray_o[parity], Ap[k].ray_d[parity], Ap[k].hit, Ap[k].queues,
+                                                    Ap[k].subcap, Ck, parity);
           if (p->profile) CU(cudaEventRecord(pev[3 * w + 1], sk));
           if (ref_rng) k_shade<RNG_REFERENCE><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], Ck, parity);
           else k_shade<RNG_PHILOX><<<Gs[k], B, 0, sk>>>(s->dscene, Pp[k], Ap[k], Ck, parity);

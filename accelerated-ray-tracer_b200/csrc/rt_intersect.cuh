@@ -365,15 +365,16 @@ RT_D void leaf_accept(const DScene& S, uint32_t ref, uint32_t entry, float t, in
 // lo is >= the parent's lo >= best.t >= its hi): skipping it changes no result and no ray count, only the number of node
 // phases a warp runs. A/B against -DRT_NO_STACK_CULL (tools/gpu_cull.sh, same box): C4 4526 -> 4661 Mrays/s (+3.0 %),
 // C5 at 10^6 spheres 3210 -> 3264 (+1.7 %), Cornell box 6295 -> 6226 (-1 %: three nodes, nothing to drop).
-#if !defined(RT_NO_STACK_CULL) && !defined(RT_STACK_CULL)
-#define RT_STACK_CULL
-#endif
-#ifdef RT_STACK_CULL
-typedef uint2 StackEnt;     // (node index, key)
+// Scenes whose BVH is a handful of nodes (both Cornell boxes: 3) have nothing to drop and pay for the check (-1 % / -3 %):
+// they run the instantiation without it (TravT<false>, k_trace_small; RT_CULL_MIN_NODES in rt_host.cu).
+#ifdef RT_NO_STACK_CULL
+#define RT_CULL_DEFAULT false
 #else
-typedef uint32_t StackEnt;  // node index
+#define RT_CULL_DEFAULT true
 #endif
-#define RT_TRAV_ARRAYS(name) StackEnt name##_stack[RT_STACK]; uint32_t name##_lq_ref[RT_LEAFQ], name##_lq_tlp[RT_LEAFQ], name##_mq_tlp[RT_MEDQ]; \
+template <bool CULL> struct StackEntT { typedef uint32_t type; };  // node index
+template <> struct StackEntT<true> { typedef uint2 type; };        // (node index, key)
+#define RT_TRAV_ARRAYS(name, CULL) typename StackEntT<CULL>::type name##_stack[RT_STACK]; uint32_t name##_lq_ref[RT_LEAFQ], name##_lq_tlp[RT_LEAFQ], name##_mq_tlp[RT_MEDQ]; \
   float name##_lq_tn[RT_LEAFQ], name##_mq_tn[RT_MEDQ]
 #define RT_TRAV_ARGS(name) name##_stack, name##_lq_ref, name##_lq_tlp, name##_lq_tn
 
@@ -397,27 +398,29 @@ RT_D void slab2(const float4 p, float o, float inv, float* out) {
 
 // Per-lane traversal state. The warp-level driver (closest_hit below for one ray per lane; k_trace's loop, which also
 // refills finished lanes with new rays) decides by ballot which phase runs next.
-struct Trav {
+template <bool CULL>
+struct TravT {
+  typedef typename StackEntT<CULL>::type StackEnt;
   Ray r;
   float ix, iy, iz;      // 1.0f / direction, aabb.cuh:48
   float tmin;
   Best best;
   int sp, nl, nm;        // stack entries, pending leaves, deferred media
   uint32_t cur;          // node to expand next, RT_NODE_EMPTY: none
-#ifdef RT_STACK_CULL
-  uint32_t cur_key;      // its sort key (0 for the root)
+  uint32_t cur_key;      // CULL: its sort key (0 for the root)
   // lo with its low two bits cleared is <= lo: a node is dropped only when lo >= best.t for certain (positive floats order like their bits)
   RT_D bool live(uint32_t key) const { return (key & ~3u) < __float_as_uint(best.t); }
-  RT_D void pop_live(const StackEnt* stack) {
+  RT_D void pop_live(const uint2* stack) {
     cur = RT_NODE_EMPTY;
     while (sp > 0) {
-      const StackEnt e = stack[--sp];
+      const uint2 e = stack[--sp];
       if (live(e.y)) { cur = e.x; cur_key = e.y; break; }
     }
   }
   // after a phase that may have brought best.t down: the node chosen before it may be behind the hit now
-  RT_D void revalidate(const StackEnt* stack) { if (have() && !live(cur_key)) pop_live(stack); }
-#endif
+  RT_D void revalidate(const StackEnt* stack) {
+    if constexpr (CULL) { if (have() && !live(cur_key)) pop_live(stack); }
+  }
   RT_D bool have() const { return cur != RT_NODE_EMPTY; }
 
   RT_D void reset() { nl = 0; nm = 0; sp = 0; cur = RT_NODE_EMPTY; best.t = FLT_MAX; best.e = RT_NO_ENTRY; }
@@ -426,9 +429,7 @@ struct Trav {
     best.t = tmax0; best.e = RT_NO_ENTRY;
     ix = frcp(r.d.x); iy = frcp(r.d.y); iz = frcp(r.d.z);
     sp = 0; nl = 0; nm = 0; cur = 0;
-#ifdef RT_STACK_CULL
-    cur_key = 0u;
-#endif
+    if constexpr (CULL) cur_key = 0u;
   }
   RT_D bool can_expand() const { return have() && nl <= RT_LEAFQ - 4; }
   RT_D bool finished() const { return !have() && nl == 0; }
@@ -488,11 +489,8 @@ struct Trav {
       if (key[k] != 0xFFFFFFFFu) {
         const uint32_t i = key[k] & 3u;
         const uint32_t c = (i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0]);
-#ifdef RT_STACK_CULL
-        stack[sp++] = make_uint2(c & 0x7FFFFFFFu, key[k]);
-#else
-        stack[sp++] = c & 0x7FFFFFFFu;
-#endif
+        if constexpr (CULL) stack[sp++] = make_uint2(c & 0x7FFFFFFFu, key[k]);
+        else stack[sp++] = c & 0x7FFFFFFFu;
       }
     }
     uint32_t next = RT_NODE_EMPTY;
@@ -501,12 +499,12 @@ struct Trav {
       next = ((i & 2u) ? ((i & 1u) ? cr[3] : cr[2]) : ((i & 1u) ? cr[1] : cr[0])) & 0x7FFFFFFFu;
     }
     cur = next;
-#ifdef RT_STACK_CULL
-    cur_key = key[0];
-    if (next == RT_NODE_EMPTY) pop_live(stack);
-#else
-    if (next == RT_NODE_EMPTY && sp > 0) cur = stack[--sp];
-#endif
+    if constexpr (CULL) {
+      cur_key = key[0];
+      if (next == RT_NODE_EMPTY) pop_live(stack);
+    } else {
+      if (next == RT_NODE_EMPTY && sp > 0) cur = stack[--sp];
+    }
   }
 
   // ---------------- leaf phase (the whole warp) ----------------
@@ -569,11 +567,12 @@ struct Trav {
     return mleaf == 0u || (__popc(mexp) >= RT_NODE_MIN && __popc(mwait) < RT_LEAF_WAIT_MAX);
   }
 };
+typedef TravT<RT_CULL_DEFAULT> Trav;
 
 // One ray per lane, no refill (k_aov, k_finish): the whole warp calls it, lanes without a ray pass active = false.
 RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, float tmax0, unsigned int* overflow) {
   Trav T;
-  RT_TRAV_ARRAYS(m);
+  RT_TRAV_ARRAYS(m, RT_CULL_DEFAULT);
   T.reset();
   if (active) T.begin(r, tmin, tmax0);
   bool flush = false;  // warp-uniform: a deferred media list is nearly full
@@ -586,9 +585,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
       if (__any_sync(0xFFFFFFFFu, T.nm > 0)) T.media_phase(S, m_mq_tlp, m_mq_tn, true);
       flush = false;
       if (done) break;
-#ifdef RT_STACK_CULL
       T.revalidate(m_stack);
-#endif
       continue;
     }
     const unsigned mwait = __ballot_sync(0xFFFFFFFFu, !T.have() && T.nl > 0);  // traversal done, leaves pending
@@ -598,9 +595,7 @@ RT_D Hit closest_hit(const DScene& S, const Ray& r, bool active, float tmin, flo
     } else {
       if ((threadIdx.x & 31) == 0) RT_COUNT(5, 1);
       flush = T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn, m_mq_tlp, m_mq_tn);
-#ifdef RT_STACK_CULL
       T.revalidate(m_stack);
-#endif
     }
   }
   return T.best.resolve(S);

@@ -204,8 +204,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_init(DScene S, RenderParams P, Pat
                             // 3.48 Grays/s against 4.04: every partial refill runs the refill, media-phase and binning code at
                             // 8..16 of 32 lanes, and issue utilisation fell from 66% to 55% (long-scoreboard stalls 3.0 -> 4.6).
 #endif
-__global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, float tmin, const float4* ray_o, const float4* ray_d,
-                                                                    float2* hit, int* queues, int subcap, WaveCounters* C, int parity) {
+template <bool CULL>
+RT_D void trace_ranges(const DScene& S, float tmin, const float4* ray_o, const float4* ray_d, float2* hit, int* queues, int subcap,
+                       WaveCounters* C, int parity) {
+  typedef TravT<CULL> Trav;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
   int next = base;  // warp-uniform: first ray of the range nobody has taken yet
   int gid = -1;     // the ray this lane is tracing
   Trav T;
-  RT_TRAV_ARRAYS(m);
+  RT_TRAV_ARRAYS(m, CULL);
   T.reset();
   bool flush = false;  // warp-uniform: a deferred media list is nearly full
   while (true) {
@@ -234,9 +236,7 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
       if (flush || __any_sync(0xFFFFFFFFu, T.nm > 0)) {
         T.media_phase(S, m_mq_tlp, m_mq_tn, true);
         flush = false;
-#ifdef RT_STACK_CULL
         T.revalidate(m_stack);
-#endif
         continue;
       }
     }
@@ -248,9 +248,7 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
     if (flush || (refill && __any_sync(0xFFFFFFFFu, fin && T.nm > 0))) {
       T.media_phase(S, m_mq_tlp, m_mq_tn, flush || fin);
       flush = false;
-#ifdef RT_STACK_CULL
       T.revalidate(m_stack);
-#endif
       continue;
     }
 #endif
@@ -294,9 +292,7 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
     } else {
       if (lane == 0) RT_COUNT(5, 1);
       flush = T.leaf_phase(S, m_lq_ref, m_lq_tlp, m_lq_tn, m_mq_tlp, m_mq_tn);
-#ifdef RT_STACK_CULL
       T.revalidate(m_stack);
-#endif
     }
   }
 #if RT_RANGE <= 64
@@ -370,6 +366,18 @@ __global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, fl
     }
   }
 #endif
+}
+__global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace(DScene S, float tmin, const float4* ray_o, const float4* ray_d,
+                                                                    float2* hit, int* queues, int subcap, WaveCounters* C, int parity) {
+  trace_ranges<RT_CULL_DEFAULT>(S, tmin, ray_o, ray_d, hit, queues, subcap, C, parity);
+}
+#ifndef RT_CULL_MIN_NODES
+#define RT_CULL_MIN_NODES 16  // C2 / C3 (3 nodes): 6286 / 5947 Mrays/s with the check, 6351 / 6133 without; every other config has >= 233 nodes
+#endif
+// The same for scenes of a handful of BVH nodes, without the stack entries' distances (nothing to drop there; rt_host.cu picks)
+__global__ void __launch_bounds__(RT_TBLOCK, RT_TRACE_MINB) k_trace_small(DScene S, float tmin, const float4* ray_o, const float4* ray_d,
+                                                                          float2* hit, int* queues, int subcap, WaveCounters* C, int parity) {
+  trace_ranges<false>(S, tmin, ray_o, ray_d, hit, queues, subcap, C, parity);
 }
 
 // One event of a path (main.cu:57-83): the hit `hh` of ray r is shaded - miss / background, emission, scatter, throughput.

@@ -352,13 +352,15 @@ def test_full_size_c4_image_does_not_depend_on_the_schedule(pyrt, monkeypatch):
     """BASELINE config C4 at its FULL resolution (800x800, 24 samples per pixel = 15 M samples, 74 M rays), through properties
     that hold at any size: the image and the ray count of the counter-based mode are functions of (seed, pixel, sample,
     bounce) alone, so they do not move by a bit with the number of paths in flight, the number of path pools, the host's
-    check interval, the hand-over to the tail kernel, or a split of the sample numbers into two progressive passes."""
+    check interval, the hand-over to the tail kernel, which of the two trace kernels runs (with / without dropping stack
+    entries that lie behind the hit), or a split of the sample numbers into two progressive passes."""
     with _scene(pyrt, 9, 800, 800) as sc:
         st = sc.render(spp=24, rng_mode=0)
         base, rays = sc.framebuffer(), st.rays
         assert st.nonfinite_samples == 0 and st.stack_overflow == 0 and st.samples == 800 * 800 * 24
         assert abs(rays / st.samples - 4.84) < 0.03   # the reference's counted bounce loop: 4.8418 rays per sample on this scene
-        for env in ({"RT_POOLS": "1"}, {"RT_POOLS": "3", "RT_WAVE_BATCH": "1"}, {"RT_TAIL_RAYS": "0"}, {"RT_TAIL_RAYS": "3000000"}):
+        for env in ({"RT_POOLS": "1"}, {"RT_POOLS": "3", "RT_WAVE_BATCH": "1"}, {"RT_TAIL_RAYS": "0"}, {"RT_TAIL_RAYS": "3000000"},
+                    {"RT_CULL_MIN_NODES": "1000000"}):   # the trace kernel that does not drop stack entries behind the hit
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             st2 = sc.render(spp=24, rng_mode=0, slots=1000000 if "RT_POOLS" in env else 0)
