@@ -157,6 +157,36 @@ def test_no_cpu_fallback(pyrt):
                     assert needle not in txt, "%s mentions %s" % (f, needle)
 
 
+def test_library_carries_native_sm100a_kernels(pyrt):
+    """The shipped library holds sm_100a machine code (no PTX-only build, no other arch) for every kernel of the path, both
+    trace kernels among them, and the node step's slab arithmetic is the packed f32x2 form (FADD2 / FMUL2, sm_100 only)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    elf = subprocess.run([cuobjdump, "-lelf", pyrt.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in elf and not [l for l in elf.splitlines() if "sm_" in l and "sm_100a" not in l], elf
+    sass = subprocess.run([cuobjdump, "-sass", pyrt.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    funcs = [l.split(":", 1)[1].strip() for l in sass.splitlines() if l.strip().startswith("Function :")]
+    for k in ("k_init", "k_traceE", "k_trace_small", "k_shade", "k_finish", "k_accumulate", "k_resolve", "k_aov", "k_ploc", "k_bvh_collapse"):
+        assert any(k in f for f in funcs), "kernel %s missing from the library" % k
+    body = {}
+    cur = None
+    for l in sass.splitlines():
+        if l.strip().startswith("Function :"):
+            cur = l.split(":", 1)[1].strip()
+            body[cur] = [0, 0]
+        elif cur and ("FADD2" in l or "FMUL2" in l):
+            body[cur][0] += 1
+        elif cur and ("STL.64" in l or "LDL.64" in l):
+            body[cur][1] += 1
+    kt = [f for f in funcs if "7k_traceE" in f][0]
+    ks = [f for f in funcs if "k_trace_small" in f][0]
+    assert body[kt][0] == 24 and body[ks][0] == 24   # 48 subtractions and multiplications of four slab tests, two per instruction
+    assert body[kt][1] > 0 and body[ks][1] == 0       # 64-bit (node, distance) stack entries only where they are dropped by distance
+
+
 def _fkey_close(a, b, tol):
     """Deep compare of SD keys: ints/strings exact, float bit patterns within `tol` ulps."""
     if isinstance(a, tuple) and isinstance(b, tuple):
