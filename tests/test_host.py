@@ -416,3 +416,65 @@ def test_leaf_order_replay_equals_the_reference_selection_sort(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "leaf_order_replay.cpp"), os.path.join(csrc, "jpeg_baseline.cpp")])
     out = subprocess.check_output([str(exe)], text=True)
     assert "sorttest: 0 mismatches" in out
+
+
+def test_stack_culling_argument_holds_in_float32():
+    """k_trace drops a stacked BVH node at pop time when its entry distance, with the two low mantissa bits cleared (they
+    carry the child slot of the sort key), is >= the closest hit found since (rt_intersect.cuh, TravT<true>::live). The
+    claim that this changes no result: the reference slab test (aabb.cuh:45-61) applied to any box INSIDE that node's box
+    - every descendant's, leaf boxes included - with t_max = that hit rejects. Checked here in float32 with the kernel's
+    own expression ((plane - o) * (1 / d), near / far plane picked by the sign of 1 / d, fmaxf / fminf that ignore NaN),
+    on nested random boxes, rays with zero direction components and origins on box planes included."""
+    rng = np.random.default_rng(7)
+    n = 400000
+    f = np.float32
+    lo_p = rng.uniform(-10, 10, (n, 3)).astype(f)
+    hi_p = (lo_p + rng.uniform(0, 8, (n, 3)).astype(f)).astype(f)
+    a, b = rng.uniform(0, 1, (n, 3)).astype(f), rng.uniform(0, 1, (n, 3)).astype(f)
+    a, b = np.minimum(a, b), np.maximum(a, b)
+    shared = rng.uniform(0, 1, (n, 3)) < 0.2           # a child often shares planes with its parent (exact unions)
+    lo_c = np.where(shared, lo_p, (lo_p + a * (hi_p - lo_p)).astype(f)).astype(f)
+    hi_c = np.where(rng.uniform(0, 1, (n, 3)) < 0.2, hi_p, (lo_p + b * (hi_p - lo_p)).astype(f)).astype(f)
+    lo_c, hi_c = np.clip(lo_c, lo_p, hi_p), np.clip(hi_c, lo_p, hi_p)
+    lo_c, hi_c = np.minimum(lo_c, hi_c), np.maximum(lo_c, hi_c)
+    o = rng.uniform(-20, 20, (n, 3)).astype(f)
+    on_plane = rng.uniform(0, 1, (n, 3)) < 0.05
+    o = np.where(on_plane, lo_p, o).astype(f)          # (plane - o) = 0: 0 * inf = NaN when the direction component is 0
+    d = rng.normal(0, 1, (n, 3)).astype(f)
+    aim = rng.uniform(0, 1, (n, 1)) < 0.7              # most rays point at the node's box, so that it is entered
+    d = np.where(aim, (lo_p + rng.uniform(0, 1, (n, 3)).astype(f) * (hi_p - lo_p) - o), d).astype(f)
+    d = np.where(rng.uniform(0, 1, (n, 3)) < 0.1, f(0), d).astype(f)
+    d = np.where(rng.uniform(0, 1, (n, 3)) < 0.02, f(-0.0), d).astype(f)
+    tmin = f(0.001)
+
+    def slab(lo, hi, tmax):
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            inv = (f(1) / d).astype(f)
+            near = np.where(inv < 0, hi, lo)
+            far = np.where(inv < 0, lo, hi)
+            tn = ((near - o).astype(f) * inv).astype(f)
+            tf = ((far - o).astype(f) * inv).astype(f)
+        t0 = np.full(n, tmin, f)
+        t1 = tmax.astype(f).copy()
+        for ax in range(3):                               # fmaxf / fminf: a NaN operand is ignored (np.fmax / np.fmin too)
+            t0 = np.fmax(tn[:, ax], t0)
+            t1 = np.fmin(tf[:, ax], t1)
+        return t0, t1
+
+    lo_parent, hi_parent = slab(lo_p, hi_p, np.full(n, np.finfo(f).max, f))
+    entered = hi_parent > lo_parent                       # the node was pushed: its box passed the test at push time
+    key = lo_parent.view(np.uint32) & np.uint32(0xFFFFFFFC)
+    for frac in (0.25, 0.9, 1.0, "1ulp", 1.1):            # a hit found later, nearer than / at / just beyond the node's entry
+        if frac == "1ulp":   # (the case that needs the two key bits cleared: with `key | slot` a node 1 ulp before the hit would go)
+            best_t, frac = np.nextafter(lo_parent, f(np.inf)), 1.0000001
+        else:
+            best_t = np.nextafter((lo_parent * f(frac)).astype(f), f(0)) if frac != 1.0 else lo_parent.copy()
+        best_t = np.maximum(best_t, np.nextafter(tmin, f(1))).astype(f)
+        dropped = entered & ~(key < best_t.view(np.uint32))
+        t0, t1 = slab(lo_c, hi_c, best_t)
+        assert not np.any(dropped & (t1 > t0)), frac      # nothing inside a dropped node would have been entered
+        if frac < 1.0:
+            assert dropped[entered & (lo_parent > tmin)].all()   # and the rule does drop the nodes behind the hit
+        elif frac > 1.0:
+            assert not dropped[entered & (lo_parent > tmin)].any()
+    assert (entered & (lo_parent > tmin)).mean() > 0.2
