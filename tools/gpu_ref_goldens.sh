@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # tools/gpu_ref_goldens.sh — run ON THE GPU BOX (via gpurun). Runs the reference's own CUDA build
 # (baseline/_ref/ref_gpu, built here by oracle/build_ref.sh) and leaves scene dumps, primary-hit ID
-# buffers, framebuffers and timings under gpurun_out/ref/. tools/make_goldens.py packs them into
+# buffers, framebuffers and timings under gpurun_out/ref/. tools/pack_goldens.py packs them into
 # tests/golden/.
 set -uo pipefail
 cd "$(dirname "$0")/.."
